@@ -1,0 +1,33 @@
+"""Scenario builders — the counterpart of gsmarl/envs/mpe_env/multiagent/scenarios/
+(GSMARL.egg-info/SOURCES.txt:20-25; reference readme.md:44 "scenario files should be
+placed in the .../scenarios directory").
+
+In the reference a scenario is a Python class with `make_world`, `reset_world`,
+`reward`, `cost`, `observation` callbacks invoked per agent per step.  Here a scenario
+is a *description*: `make_world(...)` returns a `WorldConfig`, and the four callbacks are
+evaluated inside the fused CUDA step kernel according to SPEC.md:
+    reset_world  -> SPEC §8   (gsm_reset)
+    observation  -> SPEC §6   (obs + neighbour graph)
+    reward       -> SPEC §7
+    cost         -> SPEC §7
+"""
+from .navigation import Scenario as NavigationScenario
+from .simple_formation import Scenario as PolygonScenario
+from .simple_line import Scenario as LineScenario
+
+REGISTRY = {
+    "navigation": NavigationScenario,
+    "simple_formation": PolygonScenario,   # reference file name (SOURCES.txt:24)
+    "polygon": PolygonScenario,            # readme.md:89 task name
+    "simple_line": LineScenario,           # SOURCES.txt:25
+    "line": LineScenario,
+}
+
+
+def load(name: str):
+    """Counterpart of scenarios.load(name).Scenario() in the reference's make_env.py
+    (SOURCES.txt:12)."""
+    try:
+        return REGISTRY[name]()
+    except KeyError:
+        raise KeyError(f"unknown scenario {name!r}; have {sorted(REGISTRY)}") from None
