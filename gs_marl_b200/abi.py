@@ -76,6 +76,7 @@ SYMBOLS = {
     "gsm_observe": (C.c_int, [_H, _IO, C.c_void_p]),
     "gsm_set_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_get_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gsm_host_io": (C.c_int, [_H, _IO]),
     "gsm_reset_host": (C.c_int, [_H, C.c_uint64, C.c_void_p, C.c_int64, _IO]),
     "gsm_step_host": (C.c_int, [_H, _IO]),
     "gsm_observe_host": (C.c_int, [_H, _IO]),

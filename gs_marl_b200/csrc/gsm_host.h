@@ -1,0 +1,48 @@
+// gsm_host.h — precision-agnostic launch interface between gsm_api.cu and the two
+// kernel translation units (gsm_kernels_f32.cu / gsm_kernels_f64.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gsmarl_b200.h"
+
+namespace gsm {
+
+struct HostParams {
+  int64_t n_envs, env_offset;
+  int N, L, K;
+  int scenario, action_mode, n_actions, episode_length;
+  int share_reward, cost_obstacles, own_goal_always;
+  double dt, damping, cf, km, Rs, w_dist, w_goal, goal_tol, poly_r;
+  double discrete_u[GSM_MAX_DISCRETE][2];
+  double ext[4];
+  // device arrays (typed by the handle's dtype)
+  const void* size; const uint8_t* eflag; const void* mass; const void* accel;
+  const void* max_speed; const void* slot_table;
+  void* agent_state; void* lm_pos; int32_t* t; int32_t* episode;
+};
+
+struct LaunchPlan {     // chosen once per handle
+  int cta_env;          // 1: one env per CTA; 0: packed envs per warp
+  int P;                // lanes per agent
+  int envs_per_warp;    // packed
+  int envs_per_cta;
+  size_t smem;
+  int64_t grid;
+};
+
+// Each returns a cudaError_t (as int).  physics: 1 = full step, 0 = observe only.
+int plan_f32(const HostParams& hp, LaunchPlan* plan);
+int plan_f64(const HostParams& hp, LaunchPlan* plan);
+int launch_env_f32(const HostParams& hp, const LaunchPlan& plan, const gsm_step_io& io, int physics,
+                   const uint8_t* mask, int64_t mask_stride, cudaStream_t st);
+int launch_env_f64(const HostParams& hp, const LaunchPlan& plan, const gsm_step_io& io, int physics,
+                   const uint8_t* mask, int64_t mask_stride, cudaStream_t st);
+int launch_reset_f32(const HostParams& hp, uint64_t seed, const uint8_t* mask, int64_t mask_stride,
+                     cudaStream_t st);
+int launch_reset_f64(const HostParams& hp, uint64_t seed, const uint8_t* mask, int64_t mask_stride,
+                     cudaStream_t st);
+int launch_lsa_f32(const void* cost, int32_t* col4row, int64_t n_problems, int n, cudaStream_t st);
+int launch_lsa_f64(const void* cost, int32_t* col4row, int64_t n_problems, int n, cudaStream_t st);
+
+}  // namespace gsm

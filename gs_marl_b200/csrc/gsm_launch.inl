@@ -1,0 +1,149 @@
+// gsm_launch.inl — launch glue, included by each precision's translation unit after
+// defining GSM_REAL and GSM_SFX(name).
+#include <cstdlib>
+#include <cstring>
+
+namespace gsm {
+
+static int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+// Lane efficiency of the packed mapping with P lanes per agent.
+static double packed_eff(int N, int E, int P) {
+  const int lpe = N * P;
+  if (lpe > 32) return 0.0;
+  const int epw = 32 / lpe;
+  const int iters = (E + P - 1) / P;
+  return ((double)E / (double)(P * iters)) * ((double)(epw * lpe) / 32.0);
+}
+
+int GSM_SFX(plan)(const HostParams& hp, LaunchPlan* plan) {
+  const int N = hp.N, E = hp.N + hp.L;
+  const bool lsa = hp.scenario != GSM_SCN_NAVIGATION;
+  int cta_env, P;
+  if (N <= 32) {
+    cta_env = 0; P = 1;
+    double best = packed_eff(N, E, 1);
+    for (int q = 2; q <= 4; q *= 2) {
+      const double e = packed_eff(N, E, q);
+      if (e >= best - 1e-9 && e > 0) { best = e; P = q; }
+    }
+  } else {
+    cta_env = 1; P = 32;
+  }
+  const int fm = env_int("GSM_FORCE_CTA_ENV", -1), fp = env_int("GSM_FORCE_P", 0);
+  if (fm >= 0) cta_env = fm;
+  if (fp > 0) P = fp;
+  if (P != 1 && P != 2 && P != 4 && P != 8 && P != 16 && P != 32) return (int)cudaErrorInvalidValue;
+  if (!cta_env && N * P > 32) return (int)cudaErrorInvalidValue;
+  if (lsa && N > GSM_MAX_LSA_N) return (int)cudaErrorInvalidValue;
+  plan->cta_env = cta_env;
+  plan->P = P;
+  plan->envs_per_warp = cta_env ? 0 : 32 / (N * P);
+  plan->envs_per_cta = cta_env ? 1 : plan->envs_per_warp * (kThreads / 32);
+  const SmemLayout lay = make_layout((int)sizeof(GSM_REAL), N, hp.L, E, plan->envs_per_cta, lsa ? 1 : 0);
+  plan->smem = lay.total;
+  plan->grid = (hp.n_envs + plan->envs_per_cta - 1) / plan->envs_per_cta;
+  if (plan->smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+  return 0;
+}
+
+template <int P, bool CTA_ENV, bool PHYS>
+static int launch_one(const KParams<GSM_REAL>& kp, const LaunchPlan& plan, cudaStream_t st) {
+  auto k = env_kernel<GSM_REAL, P, CTA_ENV, PHYS>;
+  if (plan.smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k<<<(unsigned)plan.grid, kThreads, plan.smem, st>>>(kp);
+  return (int)cudaGetLastError();
+}
+
+template <int P, bool CTA_ENV>
+static int launch_phys(const KParams<GSM_REAL>& kp, const LaunchPlan& plan, int physics, cudaStream_t st) {
+  return physics ? launch_one<P, CTA_ENV, true>(kp, plan, st) : launch_one<P, CTA_ENV, false>(kp, plan, st);
+}
+
+int GSM_SFX(launch_env)(const HostParams& hp, const LaunchPlan& plan, const gsm_step_io& io,
+                        int physics, const uint8_t* mask, int64_t mask_stride, cudaStream_t st) {
+  typedef GSM_REAL T;
+  if (hp.n_envs == 0) return 0;
+  KParams<T> kp;
+  std::memset(&kp, 0, sizeof(kp));
+  kp.n_envs = hp.n_envs; kp.env_offset = hp.env_offset;
+  kp.N = hp.N; kp.L = hp.L; kp.E = hp.N + hp.L; kp.K = hp.K; kp.W = (kp.E + 31) / 32;
+  kp.scenario = hp.scenario; kp.action_mode = hp.action_mode; kp.n_actions = hp.n_actions;
+  kp.episode_length = hp.episode_length;
+  kp.share_reward = hp.share_reward; kp.cost_obstacles = hp.cost_obstacles;
+  kp.own_goal_always = hp.own_goal_always;
+  kp.envs_per_warp = plan.envs_per_warp;
+  kp.dt = (T)hp.dt; kp.one_minus_damp = (T)1 - (T)hp.damping;
+  kp.cf = (T)hp.cf; kp.km = (T)hp.km; kp.Rs = (T)hp.Rs;
+  kp.w_dist = (T)hp.w_dist; kp.w_goal = (T)hp.w_goal; kp.goal_tol = (T)hp.goal_tol;
+  kp.poly_r = (T)hp.poly_r;
+  for (int a = 0; a < GSM_MAX_DISCRETE; a++) {
+    kp.discrete_u[a][0] = (T)hp.discrete_u[a][0];
+    kp.discrete_u[a][1] = (T)hp.discrete_u[a][1];
+  }
+  kp.size = (const T*)hp.size; kp.eflag = hp.eflag; kp.mass = (const T*)hp.mass;
+  kp.accel = (const T*)hp.accel; kp.max_speed = (const T*)hp.max_speed;
+  kp.slot_table = (const T*)hp.slot_table;
+  kp.agent_state = (T*)hp.agent_state; kp.lm_pos = (T*)hp.lm_pos; kp.t = hp.t;
+  kp.mask = mask; kp.mask_stride = mask_stride;
+  kp.actions = io.actions;
+  kp.obs = (T*)io.obs; kp.nbr_idx = io.nbr_idx; kp.nbr_feat = (T*)io.nbr_feat;
+  kp.nbr_cnt = io.nbr_cnt; kp.adj = io.adj; kp.reward = (T*)io.reward; kp.cost = (T*)io.cost;
+  kp.done = io.done; kp.assign = io.assign;
+  if (plan.cta_env) {
+    switch (plan.P) {
+      case 1: return launch_phys<1, true>(kp, plan, physics, st);
+      case 2: return launch_phys<2, true>(kp, plan, physics, st);
+      case 4: return launch_phys<4, true>(kp, plan, physics, st);
+      case 8: return launch_phys<8, true>(kp, plan, physics, st);
+      case 16: return launch_phys<16, true>(kp, plan, physics, st);
+      default: return launch_phys<32, true>(kp, plan, physics, st);
+    }
+  }
+  switch (plan.P) {
+    case 1: return launch_phys<1, false>(kp, plan, physics, st);
+    case 2: return launch_phys<2, false>(kp, plan, physics, st);
+    case 4: return launch_phys<4, false>(kp, plan, physics, st);
+    case 8: return launch_phys<8, false>(kp, plan, physics, st);
+    case 16: return launch_phys<16, false>(kp, plan, physics, st);
+    default: return launch_phys<32, false>(kp, plan, physics, st);
+  }
+}
+
+int GSM_SFX(launch_reset)(const HostParams& hp, uint64_t seed, const uint8_t* mask,
+                          int64_t mask_stride, cudaStream_t st) {
+  if (hp.n_envs == 0) return 0;
+  ResetParams rp;
+  std::memset(&rp, 0, sizeof(rp));
+  rp.n_envs = hp.n_envs; rp.env_offset = hp.env_offset; rp.N = hp.N; rp.L = hp.L; rp.seed = seed;
+  for (int k = 0; k < 4; k++) rp.ext[k] = hp.ext[k];
+  rp.eflag = hp.eflag; rp.mask = mask; rp.mask_stride = mask_stride;
+  rp.agent_state = hp.agent_state; rp.lm_pos = hp.lm_pos; rp.t = hp.t; rp.episode = hp.episode;
+  const int64_t total = hp.n_envs * (hp.N + hp.L);
+  reset_kernel<GSM_REAL><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  reset_counters_kernel<GSM_REAL><<<(unsigned)((hp.n_envs + 255) / 256), 256, 0, st>>>(
+      hp.n_envs, mask, mask_stride, hp.t, hp.episode);
+  return (int)cudaGetLastError();
+}
+
+int GSM_SFX(launch_lsa)(const void* cost, int32_t* col4row, int64_t n_problems, int n,
+                        cudaStream_t st) {
+  if (n_problems == 0) return 0;
+  int G = 4;
+  while (G < n) G *= 2;
+  const int threads = 128, per_cta = threads / G;
+  const size_t smem = (size_t)per_cta * n * n * sizeof(GSM_REAL);
+  lsa_kernel<GSM_REAL><<<(unsigned)((n_problems + per_cta - 1) / per_cta), threads, smem, st>>>(
+      (const GSM_REAL*)cost, col4row, n_problems, n, G);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace gsm

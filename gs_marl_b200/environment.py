@@ -1,0 +1,229 @@
+"""Batched counterparts of the reference's three env classes
+(gsmarl/envs/mpe_env/multiagent/environment.py, GSMARL.egg-info/SOURCES.txt:15;
+described in reference readme.md:27-41):
+
+    MultiAgentEnv               fixed-size obs, no cost           (readme.md:29-33)
+    MultiAgentConstrainEnv      fixed-size obs + cost             (readme.md:34-37)
+    MultiAgentGraphConstrainEnv variable-size graph obs + cost    (readme.md:38-41)
+
+One object = `n_envs` independent worlds resident on one B200; `step` is ONE fused
+kernel launch through the C ABI (include/gsmarl_b200.h).  torch is used only for device
+memory and the current stream.  The reference's per-env return convention (lists of
+per-agent arrays) becomes stacked tensors with leading dims [n_envs, n_agents].
+
+The reference source is withheld, so the exact tuple arity/order of its `step` cannot
+be checked; the order here is the one BASELINE.json's north_star states:
+`obs, graph/adjacency, rewards, costs, dones, infos`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import abi
+from .config import WorldConfig
+
+_TORCH_DT = {np.float32: torch.float32, np.float64: torch.float64, np.int32: torch.int32,
+             np.uint32: torch.int32, np.uint8: torch.uint8}
+
+
+class Box:
+    """Shape/dtype descriptor standing in for gym.spaces.Box (gym is not a dependency)."""
+
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = tuple(shape), dtype
+
+    def __repr__(self):
+        return f"Box(shape={self.shape}, dtype={np.dtype(self.dtype).name})"
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n = n
+
+    def __repr__(self):
+        return f"Discrete({self.n})"
+
+
+class MultiAgentGraphConstrainEnv:
+    OUTPUTS = ("obs", "nbr_idx", "nbr_feat", "nbr_cnt", "adj", "reward", "cost", "done", "assign")
+
+    def __init__(self, world: WorldConfig, n_envs: int, device: int = 0, env_offset: int = 0,
+                 auto_reset: bool = False, seed: int = 0):
+        self.world, self.n_envs, self.device_index = world, int(n_envs), int(device)
+        self.env_offset, self.auto_reset = int(env_offset), bool(auto_reset)
+        self.lib = abi.load_library()
+        if not torch.cuda.is_available():
+            raise abi.GsmError("CUDA device required: gs_marl_b200 has no CPU fallback")
+        self.device = torch.device("cuda", self.device_index)
+        self._c, self._keep = world.to_c()
+        self._h = C.c_void_p()
+        abi.check(self.lib, self.lib.gsm_create(C.byref(self._c), self.n_envs, self.env_offset,
+                                                self.device_index, C.byref(self._h)))
+        self._seed = int(seed)
+        self._shapes = world.io_shapes(self.n_envs)
+        self.buf = {k: self._alloc(k) for k in self.OUTPUTS}
+        self._io = self._make_io(self.buf)
+        # reference-style attributes (per agent)
+        self.n = world.n_agents
+        n, K = world.n_agents, world.max_nbrs
+        self.observation_space = [Box((abi.GSM_OBS_DIM,), world.np_real)] * n
+        self.node_observation_space = [Box((K, abi.GSM_NBR_FEAT_DIM), world.np_real)] * n
+        self.adj_observation_space = [Box((world.adj_words,), np.uint32)] * n
+        self.share_observation_space = [Box((n * abi.GSM_OBS_DIM,), world.np_real)] * n
+        self.action_space = ([Discrete(len(world.discrete_u))] * n
+                             if world.action_mode == "discrete" else [Box((2,), world.np_real)] * n)
+
+    # ---- plumbing ---------------------------------------------------------------------
+    def _alloc(self, name, lead=()):
+        dt, shape = self._shapes[name]
+        return torch.zeros(tuple(lead) + tuple(shape), dtype=_TORCH_DT[dt], device=self.device)
+
+    @staticmethod
+    def _make_io(bufs: dict, actions: Optional[torch.Tensor] = None) -> abi.GsmStepIO:
+        io = abi.GsmStepIO()
+        for k in abi.GsmStepIO.FIELDS:
+            t = actions if k == "actions" else bufs.get(k)
+            setattr(io, k, None if t is None else t.data_ptr())
+        return io
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, st):
+        abi.check(self.lib, st, self._h)
+
+    def _actions(self, actions) -> torch.Tensor:
+        dt, shape = self._shapes["actions"]
+        a = torch.as_tensor(actions, device=self.device).to(_TORCH_DT[dt]).contiguous()
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError(f"actions must have shape {tuple(shape)}, got {tuple(a.shape)}")
+        return a
+
+    def _result(self, b):
+        graph = {"nbr_idx": b["nbr_idx"], "nbr_feat": b["nbr_feat"], "nbr_cnt": b["nbr_cnt"],
+                 "adj": b["adj"]}
+        infos = {"assign": b["assign"], "collisions": b["cost"]}
+        return b["obs"], graph, b["reward"], b["cost"], b["done"], infos
+
+    # ---- reference API ----------------------------------------------------------------
+    def seed(self, seed: int):
+        self._seed = int(seed)
+
+    def reset(self, mask: Optional[torch.Tensor] = None):
+        """reset() -> obs, graph.  mask: optional uint8/bool [n_envs] (device)."""
+        m, stride = None, 1
+        if mask is not None:
+            mt = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            m = C.c_void_p(mt.data_ptr())
+        with torch.cuda.device(self.device):
+            self._check(self.lib.gsm_reset(self._h, self._seed, m, stride, C.byref(self._io),
+                                           self._stream()))
+        b = self.buf
+        return b["obs"], {"nbr_idx": b["nbr_idx"], "nbr_feat": b["nbr_feat"],
+                          "nbr_cnt": b["nbr_cnt"], "adj": b["adj"]}
+
+    def step(self, actions):
+        """step(actions) -> obs, graph, rewards, costs, dones, infos (device tensors, views of
+        buffers that the next step overwrites)."""
+        a = self._actions(actions)
+        io = self._make_io(self.buf, a)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.gsm_step(self._h, C.byref(io), self._stream()))
+            if self.auto_reset:
+                # done envs restart; their obs/graph rows become the first obs of the new
+                # episode, reward/cost/done keep the terminal step's values.
+                self._check(self.lib.gsm_reset(self._h, self._seed, C.c_void_p(self.buf["done"].data_ptr()),
+                                               self.world.n_agents, C.byref(self._io), self._stream()))
+        return self._result(self.buf)
+
+    def rollout(self, actions, out: Optional[dict] = None) -> dict:
+        """T steps from one CUDA-graph launch; actions [T, n_envs, N(,2)]; returns dict of
+        [T, ...] tensors (the rollout-buffer layout)."""
+        dt, shape = self._shapes["actions"]
+        a = torch.as_tensor(actions, device=self.device).to(_TORCH_DT[dt]).contiguous()
+        T = a.shape[0]
+        if tuple(a.shape[1:]) != tuple(shape):
+            raise ValueError(f"actions must have shape (T,)+{tuple(shape)}")
+        if out is None:
+            out = {k: self._alloc(k, (T,)) for k in self.OUTPUTS}
+        io = self._make_io(out, a)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.gsm_rollout(self._h, T, C.byref(io), self._stream()))
+        out["actions"] = a
+        return out
+
+    def observe(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.gsm_observe(self._h, C.byref(self._io), self._stream()))
+        return self._result(self.buf)[:2]
+
+    # ---- state access (parity tests, checkpoint/resume) ---------------------------------
+    def state_tensors(self):
+        w, r = self.world, _TORCH_DT[self.world.np_real]
+        return (torch.zeros((self.n_envs, w.n_agents, 4), dtype=r, device=self.device),
+                torch.zeros((self.n_envs, w.n_landmarks, 2), dtype=r, device=self.device),
+                torch.zeros((self.n_envs,), dtype=torch.int32, device=self.device))
+
+    def set_state(self, agent_state=None, landmark_pos=None, step_count=None):
+        r = _TORCH_DT[self.world.np_real]
+
+        def prep(x, dt):
+            return None if x is None else torch.as_tensor(x).to(device=self.device, dtype=dt).contiguous()
+        a, l, t = prep(agent_state, r), prep(landmark_pos, r), prep(step_count, torch.int32)
+        p = [C.c_void_p(x.data_ptr()) if x is not None and x.numel() else None for x in (a, l, t)]
+        with torch.cuda.device(self.device):
+            self._check(self.lib.gsm_set_state(self._h, p[0], p[1], p[2], self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def get_state(self):
+        a, l, t = self.state_tensors()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.gsm_get_state(self._h, a.data_ptr(), l.data_ptr() if l.numel() else None,
+                                               t.data_ptr(), self._stream()))
+        return a, l, t
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.gsm_kernel_launches(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.gsm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiAgentConstrainEnv(MultiAgentGraphConstrainEnv):
+    """Fixed-size observation + cost (readme.md:34-37).  The fixed-size observation is the
+    agent's own 6 features followed by its K padded neighbour rows, flattened
+    [DECL: the reference's fixed layout is unknown]."""
+
+    def _flat_obs(self, b):
+        n_envs, N = self.n_envs, self.world.n_agents
+        return torch.cat([b["obs"], b["nbr_feat"].reshape(n_envs, N, -1)], dim=-1)
+
+    def reset(self, mask=None):
+        super().reset(mask)
+        return self._flat_obs(self.buf)
+
+    def step(self, actions):
+        super().step(actions)
+        b = self.buf
+        return self._flat_obs(b), b["reward"], b["cost"], b["done"], {"assign": b["assign"]}
+
+
+class MultiAgentEnv(MultiAgentConstrainEnv):
+    """Fixed-size observation, no cost (readme.md:29-33)."""
+
+    def step(self, actions):
+        obs, rew, _cost, done, infos = super().step(actions)
+        return obs, rew, done, infos

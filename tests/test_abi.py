@@ -1,0 +1,99 @@
+"""The C-ABI boundary without a GPU: the library loads, exports every symbol the header
+declares, validates configs, and refuses loudly (no CPU fallback) when there is no device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from gs_marl_b200 import abi
+from tests._util import make_cfg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "gsmarl_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gsm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = abi.load_library()
+    names = header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(abi.SYMBOLS) == names          # python table == header
+    assert lib.gsm_abi_version() == abi.GSM_ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    assert C.sizeof(abi.GsmConfig) == 224
+    assert C.sizeof(abi.GsmStepIO) == 80
+    assert abi.GsmConfig.dt.offset == 56 and abi.GsmConfig.discrete_u.offset == 160
+
+
+def _create(cfg, n_envs=4):
+    lib = abi.load_library()
+    c, keep = cfg.to_c()
+    h = C.c_void_p()
+    st = lib.gsm_create(C.byref(c), n_envs, 0, 0, C.byref(h))
+    msg = lib.gsm_last_error(None).decode()
+    if st == 0:
+        lib.gsm_destroy(h)
+    return st, msg
+
+
+def test_invalid_configs_are_rejected_before_touching_a_device():
+    good = make_cfg("navigation", 3, "f32")
+    for kw, frag in [({"max_nbrs": 0}, "max_nbrs"), ({"max_nbrs": 99}, "max_nbrs"),
+                     ({"dt": 0.0}, "dt"), ({"contact_margin": 0.0}, "contact_margin"),
+                     ({"episode_length": 0}, "episode_length"),
+                     ({"mass": [1.0, 0.0, 1.0]}, "mass"),
+                     ({"type": [0, 0, 1, 1, 1, 1, 2, 2, 2]}, "agents must be")]:
+        st, msg = _create(good.replace(**kw))
+        assert st == -1 and frag in msg, (kw, st, msg)
+    st, msg = _create(make_cfg("polygon", 4, "f32").replace(n_landmarks=2, size=[0.1] * 6, collide=[1] * 6,
+                                                            type=[0, 0, 0, 0, 3, 3], max_nbrs=3))
+    assert st == -1 and "polygon" in msg
+
+
+def test_abi_version_mismatch():
+    lib = abi.load_library()
+    c, keep = make_cfg("navigation", 3, "f32").to_c()
+    c.abi_version = 1
+    h = C.c_void_p()
+    assert lib.gsm_create(C.byref(c), 4, 0, 0, C.byref(h)) == -3
+    c.abi_version = abi.GSM_ABI_VERSION
+    c.struct_size = 8
+    assert lib.gsm_create(C.byref(c), 4, 0, 0, C.byref(h)) == -3
+
+
+def test_no_device_means_error_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    st, msg = _create(make_cfg("navigation", 3, "f32"))
+    assert st == -5 and "no CPU fallback" in msg
+    from gs_marl_b200.environment import MultiAgentGraphConstrainEnv
+    with pytest.raises(abi.GsmError):
+        MultiAgentGraphConstrainEnv(make_cfg("navigation", 3, "f32"), 4)
+    from gs_marl_b200.env_wrappers import GraphVecEnv
+    with pytest.raises(abi.GsmError):
+        GraphVecEnv(make_cfg("navigation", 3, "f32"), 4)
+
+
+def test_missing_library_raises(tmp_path):
+    with pytest.raises(abi.GsmError):
+        abi.load_library(str(tmp_path / "nope.so"))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gs_marl_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inl")):
+                s = open(os.path.join(d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", s, flags=re.M), f
+                assert "gsm_oracle" not in s, f

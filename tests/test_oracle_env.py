@@ -1,0 +1,109 @@
+"""The oracle against what it can be pinned to.
+
+* Philox4x32-10: Random123 known-answer vectors (a real external KAT).
+* C oracle vs the committed golden trajectories (tests/golden/traj_*.npz, produced by the
+  independent pure-Python restatement oracle/py_env.py with np.logaddexp and scipy's LSA).
+* C oracle vs py_env live on fresh seeds.
+
+PARITY UNPINNED vs GS-MARL: the reference's env sources are withheld and it ships no
+tests or vectors; these tests pin the oracle to SPEC.md only.
+"""
+import numpy as np
+import pytest
+
+from oracle import gsm_oracle as O, py_env
+from tests._util import GOLDEN_TRAJ, golden_path, make_cfg, assert_match, random_actions
+
+
+def test_philox_known_answers():
+    kat = [((0, 0, 0, 0, 0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 6, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for args, want in kat:
+        assert tuple(int(x) for x in O.philox(*args)) == want
+
+
+@pytest.mark.parametrize("name,N,kw", GOLDEN_TRAJ)
+def test_c_oracle_matches_golden(name, N, kw):
+    z = np.load(golden_path(name, N, kw))
+    cfg = make_cfg(name, N, "f64", **kw)
+    B, T = z["actions"].shape[1], z["actions"].shape[0]
+    env = O.OracleEnv(cfg, B)
+    env.set_state(z["agent_state0"], z["landmark_pos"], np.zeros(B, np.int32))
+    for t in range(T):
+        out = env.step(z["actions"][t])
+        want = {k: z[k][t] for k in ("obs", "nbr_idx", "nbr_feat", "nbr_cnt", "adj", "reward",
+                                     "cost", "done", "assign")}
+        assert_match(out, want, rtol=1e-12, atol=1e-13, ctx=f"{name}{N} t={t}")
+        np.testing.assert_allclose(env.agent_state, z["agent_state"][t], rtol=1e-12, atol=1e-13)
+    assert z["cost"].sum() > 0          # the fixtures do exercise collisions
+
+
+@pytest.mark.parametrize("name,N,kw", [("navigation", 5, {}), ("polygon", 7, {"share_reward": True}),
+                                       ("line", 3, {}), ("navigation", 2, {"cost_obstacles": False})])
+def test_c_oracle_matches_py_env_live(name, N, kw):
+    cfg = make_cfg(name, N, "f64", **kw)
+    rng = np.random.default_rng(3)
+    B = 3
+    env = O.OracleEnv(cfg, B)
+    env.reset(99)
+    env.agent_state *= 0.5
+    env.landmark_pos *= 0.5
+    pes = [py_env.PyEnv(cfg) for _ in range(B)]
+    for b, p in enumerate(pes):
+        p.set_state(env.agent_state[b], env.landmark_pos[b])
+    for t in range(8):
+        a = random_actions(cfg, rng, (B,))
+        out = env.step(a)
+        for b, p in enumerate(pes):
+            po = p.step(a[b])
+            assert_match({k: v[b] for k, v in out.items()}, po, rtol=1e-12, atol=1e-13,
+                         ctx=f"{name}{N} t={t} b={b}")
+
+
+def test_reset_is_shard_invariant_and_masked():
+    cfg = make_cfg("navigation", 3, "f64")
+    full = O.OracleEnv(cfg, 8)
+    full.reset(42)
+    lo = O.OracleEnv(cfg, 3, env_offset=0)
+    hi = O.OracleEnv(cfg, 5, env_offset=3)
+    lo.reset(42)
+    hi.reset(42)
+    assert (np.concatenate([lo.agent_state, hi.agent_state]) == full.agent_state).all()
+    assert (np.concatenate([lo.landmark_pos, hi.landmark_pos]) == full.landmark_pos).all()
+    before = full.agent_state.copy()
+    mask = np.array([1, 0, 0, 1, 0, 0, 0, 0], np.uint8)
+    full.reset(42, mask)
+    assert (full.agent_state[1:3] == before[1:3]).all() and (full.agent_state[4:] == before[4:]).all()
+    assert (full.agent_state[0] != before[0]).any()        # new episode -> new draw
+    assert (full.episode == np.array([2, 1, 1, 2, 1, 1, 1, 1])).all()
+    ext = cfg.spawn_extent[0]
+    assert (np.abs(full.agent_state[..., :2]) <= ext).all() and (full.agent_state[..., 2:] == 0).all()
+
+
+def test_f32_oracle_tracks_f64_one_step():
+    cfg64 = make_cfg("navigation", 6, "f64")
+    cfg32 = cfg64.replace(dtype="f32")
+    e64, e32 = O.OracleEnv(cfg64, 16), O.OracleEnv(cfg32, 16)
+    e64.reset(5)
+    e32.set_state(e64.agent_state, e64.landmark_pos)
+    a = random_actions(cfg64, np.random.default_rng(0), (16,))
+    o64, o32 = e64.step(a), e32.step(a)
+    np.testing.assert_allclose(o32["obs"], o64["obs"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(o32["reward"], o64["reward"], rtol=1e-4, atol=1e-5)
+
+
+def test_threads_give_identical_results():
+    cfg = make_cfg("navigation", 4, "f64")
+    a = random_actions(cfg, np.random.default_rng(1), (64,))
+    outs = []
+    for nt in (1, 4):
+        O.set_threads(nt)
+        e = O.OracleEnv(cfg, 64)
+        e.reset(8)
+        outs.append((e.step(a), e.agent_state.copy()))
+    O.set_threads(1)
+    for k in outs[0][0]:
+        assert (outs[0][0][k] == outs[1][0][k]).all()
+    assert (outs[0][1] == outs[1][1]).all()
