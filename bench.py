@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/s of the batched GS-MARL env hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (this repo's arm)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm)
+
+A "step" is one env step of the whole batch: BASELINE.json configs[1] — cooperative
+navigation, 3 agents, 16384 envs per GPU, random discrete actions — in the production
+precision (fp32).  `value` is device-resident throughput (actions already in HBM, outputs
+written to a rotating 25-slot rollout buffer larger than L2, 25 steps per CUDA-graph
+launch).  `e2e` is the same metric through the numpy-facing drop-in (`GraphVecEnv.step`):
+host actions in, host outputs out, both copies inside the timed region.
+
+IMPORTANT LABEL: the GS-MARL env sources are withheld (reference readme.md:1), so the
+model is the declared one of SPEC.md with the UNVERIFIED constants of
+gs_marl_b200/presets.py, and the CPU arm is this repo's reference-STYLE numpy port
+(oracle/py_env.py: one Python env object per world, subprocess workers), not GS-MARL's
+own code.  Every JSON line says so in `config.spec_status`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_AGENTS = 3
+ENVS_PER_GPU = 16384
+ROLLOUT_T = 25
+SPEC_STATUS = ("declared model (SPEC.md) with UNVERIFIED constants; GS-MARL env sources withheld, "
+               "parity with the reference unpinned")
+METRIC = "agent-steps/sec (graph obs+reward+cost)"
+UNIT = "agent-steps/s"
+
+
+def workload_config(n_gpus, extra=None):
+    c = {"workload": f"cooperative navigation, {N_AGENTS} agents, {ENVS_PER_GPU} envs per GPU, "
+                     "random discrete actions, fp32 production mode",
+         "n_agents": N_AGENTS, "envs_per_gpu": ENVS_PER_GPU, "global_envs": ENVS_PER_GPU * n_gpus,
+         "parallelism": f"env-sharded x{n_gpus}, no collective on the step path",
+         "spec_status": SPEC_STATUS}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arm: reference-STYLE numpy port in subprocess workers (SubprocVecEnv lineage)
+def _cpu_worker(conn, n_envs, seed):
+    import numpy as np
+    from gs_marl_b200 import scenarios
+    from oracle import gsm_oracle as O, py_env
+    cfg = scenarios.load("navigation").make_world(N_AGENTS, dtype="f64")
+    init = O.OracleEnv(cfg, n_envs, env_offset=seed * 100003)
+    init.reset(1)
+    envs = [py_env.PyEnv(cfg) for _ in range(n_envs)]
+    for b, e in enumerate(envs):
+        e.set_state(init.agent_state[b], init.landmark_pos[b])
+    rng = np.random.default_rng(seed)
+    conn.send("ready")
+    while True:
+        cmd = conn.recv()
+        if cmd == "close":
+            break
+        acts = rng.integers(0, 5, (n_envs, N_AGENTS))
+        outs = [e.step(acts[b]) for b, e in enumerate(envs)]
+        # stack like the vec-env wrapper does (obs, graph, reward, cost, done per env)
+        stacked = {k: np.stack([o[k] for o in outs]) for k in outs[0]}
+        conn.send(float(stacked["reward"].sum()))
+    conn.close()
+
+
+class CpuVecEnv:
+    def __init__(self, n_envs, cores):
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        self.cores = max(1, min(cores, n_envs))
+        per = [n_envs // self.cores + (1 if r < n_envs % self.cores else 0) for r in range(self.cores)]
+        self.n_envs = n_envs
+        self.conns, self.procs = [], []
+        for r, m in enumerate(per):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_cpu_worker, args=(b, m, r), daemon=True)
+            p.start()
+            self.conns.append(a); self.procs.append(p)
+        for c in self.conns:
+            assert c.recv() == "ready"
+
+    def step(self):
+        for c in self.conns:
+            c.send("step")
+        return sum(c.recv() for c in self.conns)
+
+    def close(self):
+        for c in self.conns:
+            c.send("close")
+        for p in self.procs:
+            p.join(5)
+
+
+def cpu_rate(total_budget_s, n_steps):
+    """agent-steps/s of the reference-style port on all host cores, on a bounded sample sized
+    so that n_steps steps take about total_budget_s."""
+    cores = os.cpu_count() or 1
+    probe = CpuVecEnv(cores * 2, cores)
+    probe.step()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        probe.step()
+    per_env_step = (time.perf_counter() - t0) / 3 / 2          # seconds per env-step per core
+    probe.close()
+    envs = int(max(cores, min(ENVS_PER_GPU, total_budget_s / max(n_steps, 1) / per_env_step * cores)))
+    return cores, envs
+
+
+def cpu_c_oracle_rate(seconds=3.0):
+    """The C restatement of the same model on all cores (a much stronger CPU baseline than the
+    reference's Python style) — reported for context."""
+    import numpy as np
+    from gs_marl_b200 import scenarios
+    from oracle import gsm_oracle as O
+    cores = os.cpu_count() or 1
+    O.set_threads(cores)
+    cfg = scenarios.load("navigation").make_world(N_AGENTS, dtype="f32")
+    env = O.OracleEnv(cfg, ENVS_PER_GPU)
+    env.reset(1)
+    bufs = env.alloc_io()
+    a = np.random.default_rng(0).integers(0, 5, (ENVS_PER_GPU, N_AGENTS)).astype(np.int32)
+    env.step(a, bufs)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        env.step(a, bufs); n += 1
+    dt = time.perf_counter() - t0
+    O.set_threads(1)
+    return {"value": n * ENVS_PER_GPU * N_AGENTS / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"C oracle (oracle/gsm_oracle.c, fp32), {ENVS_PER_GPU} envs x {n} steps, pthreads"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = args.steps, args.warmup
+    cores, envs = cpu_rate(args.ref_budget, steps + warm)
+    vec = CpuVecEnv(envs, cores)
+    for _ in range(warm):
+        vec.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        vec.step()
+    dt = time.perf_counter() - t0
+    vec.close()
+    value = envs * N_AGENTS * steps / dt
+    sample = (f"reference-STYLE numpy port (oracle/py_env.py; GS-MARL's own env is withheld), fp64, "
+              f"{envs} envs per step in {cores} subprocess workers, {steps} steps")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, {"sample_envs_per_step": envs}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from gs_marl_b200 import scenarios
+    from gs_marl_b200.environment import MultiAgentGraphConstrainEnv
+    from gs_marl_b200.env_wrappers import GraphVecEnv, ShardedStats
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W, T = args.steps, args.warmup, ROLLOUT_T
+    cfg = scenarios.load("navigation").make_world(N_AGENTS, dtype="f32", episode_length=T)
+    env = MultiAgentGraphConstrainEnv(cfg, args.envs, device=local, env_offset=rank * args.envs, seed=1)
+    env.reset()
+    gen = torch.Generator(device=dev); gen.manual_seed(rank)
+    acts = torch.randint(0, 5, (T, args.envs, N_AGENTS), generator=gen, device=dev, dtype=torch.int32)
+    ring = {k: env._alloc(k, (T,)) for k in env.OUTPUTS}       # rollout buffer, T slots
+    ring_bytes = sum(v.numel() * v.element_size() for v in ring.values())
+
+    def run_steps(n):
+        done = 0
+        while done + T <= n:
+            env.reset()                      # new episode every T steps (episode_length == T)
+            env.rollout(acts, out=ring)
+            done += T
+        if done < n:
+            env.reset()
+            for s in range(n - done):
+                io_bufs = {k: v[s] for k, v in ring.items()}
+                io = env._make_io(io_bufs, acts[s])
+                env._check(env.lib.gsm_step(env._h, __import__("ctypes").byref(io), env._stream()))
+
+    run_steps(max(W, 3))
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = env.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    run_steps(K)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = env.kernel_launches - l0
+    n_resets = (K + T - 1) // T
+    clocks = sampler.stop()
+
+    # dominant kernel alone: K env-kernel launches, no resets, CUDA events on the same stream
+    env.reset()
+    env.rollout(acts, out=ring)
+    torch.cuda.synchronize()
+    reps = max(2, min(40, K // T))
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(reps):
+        env.rollout(acts, out=ring)
+    k1.record()
+    torch.cuda.synchronize()
+    kern_ms = k0.elapsed_time(k1) / (reps * T)
+
+    # ---- e2e through the numpy-facing drop-in ------------------------------------------------
+    vec = GraphVecEnv(cfg, args.envs, device=local, env_offset=rank * args.envs, seed=1)
+    vec.reset()
+    host_acts = np.random.default_rng(rank).integers(0, 5, (8, args.envs, N_AGENTS)).astype(np.int32)
+    stats = ShardedStats()
+    Ke = max(10, min(args.e2e_steps, K))
+    for s in range(5):
+        vec.step(host_acts[s % 8])
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(Ke):
+        obs, graph, rew, cost, done, infos = vec.step(host_acts[s % 8])
+        if s % T == T - 1:
+            vec.reset()
+    e2e_s = time.perf_counter() - t0
+    stats.add(args.envs * Ke, N_AGENTS, float(rew.sum()), float(cost.sum()), float(done.sum()))
+    h2d = host_acts[0].nbytes
+    d2h = sum(v.nbytes for k, v in vec.buf.items() if k != "actions")
+    vec.close()
+
+    tms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    totals = stats.all_reduce(device=dev)        # the only collective: final stats gather
+    ms, e2e_ms = tms.tolist()
+
+    if rank == 0:
+        agent_steps = args.envs * N_AGENTS * K * world
+        value = agent_steps / (ms * 1e-3)
+        peak, peak_src = measured_peak()
+        bytes_launch = cfg.bytes_per_agent_step() * args.envs * N_AGENTS
+        achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world, {
+                "envs_per_gpu": args.envs, "global_envs": args.envs * world,
+                "l2_policy": f"outputs rotate through a {T}-slot rollout buffer of {ring_bytes / 1e6:.0f} MB "
+                             "(> 126 MB L2); no explicit flush",
+                "episode": f"reset every {T} steps ({n_resets} resets inside the timed region)",
+                "launch": f"{T} steps per CUDA-graph launch (gsm_rollout)"}),
+            "env_steps_per_s": value / N_AGENTS,
+            "clocks": clocks,
+            "e2e": {"value": args.envs * N_AGENTS * Ke * world / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "api": "GraphVecEnv.step -> gsm_step_host (pinned arena; 1 H2D + 1 kernel + 1 D2H)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(),
+                         "kernel": "gsm::env_kernel<float,1,false,true>",
+                         "launch_us": kern_ms * 1e3, "algorithmic_bytes_per_launch": bytes_launch,
+                         "bytes_per_agent_step": cfg.bytes_per_agent_step(), "peak_source": peak_src,
+                         "note": "layout is the declared one of SPEC.md §6 (reference layout unknown)"},
+            "final_stats": totals,
+        }
+        if world == 1 and not args.no_cpu:
+            cores, envs = cpu_rate(args.cpu_budget, 10)
+            cvec = CpuVecEnv(envs, cores)
+            cvec.step()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                cvec.step()
+            dt = time.perf_counter() - t0
+            cvec.close()
+            line["cpu_baseline"] = {
+                "value": envs * N_AGENTS * 10 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"reference-STYLE numpy port (oracle/py_env.py; GS-MARL's own env is withheld), "
+                          f"fp64, {envs} envs x 10 steps in {cores} subprocess workers"}
+            line["cpu_baseline_c_port"] = cpu_c_oracle_rate()
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--ref-budget", type=float, default=90.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
