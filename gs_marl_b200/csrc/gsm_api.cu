@@ -174,6 +174,32 @@ int do_env(gsm_env* h, const gsm_step_io& io, int physics, const uint8_t* mask, 
   return 0;
 }
 
+// One env step (physics + outputs): the size-specialised kernel when the handle has one.
+int do_steps(gsm_env* h, const gsm_step_io& io, int n_steps, cudaStream_t st) {
+  gsm::RolloutStrides rs;
+  std::memset(&rs, 0, sizeof(rs));
+  if (n_steps > 1) {
+    rs.actions = (int64_t)h->io_bytes[IO_ACTIONS]; rs.obs = (int64_t)h->io_bytes[IO_OBS];
+    rs.nbr_idx = (int64_t)h->io_bytes[IO_NBR_IDX]; rs.nbr_feat = (int64_t)h->io_bytes[IO_NBR_FEAT];
+    rs.nbr_cnt = (int64_t)h->io_bytes[IO_NBR_CNT]; rs.adj = (int64_t)h->io_bytes[IO_ADJ];
+    rs.reward = (int64_t)h->io_bytes[IO_REWARD]; rs.cost = (int64_t)h->io_bytes[IO_COST];
+    rs.done = (int64_t)h->io_bytes[IO_DONE]; rs.assign = (int64_t)h->io_bytes[IO_ASSIGN];
+  }
+  const int e = is_f32(h) ? gsm::launch_spec_f32(h->hp, io, n_steps, rs, st)
+                          : gsm::launch_spec_f64(h->hp, io, n_steps, rs, st);
+  if (e > 0) return cuda_fail(h, e, "specialised env kernel launch");
+  if (e == 0) { h->launches += 1; return 0; }
+  return -1000;      // no instance
+}
+
+int do_step(gsm_env* h, const gsm_step_io& io, cudaStream_t st) {
+  if (h->plan.spec) {
+    const int r = do_steps(h, io, 1, st);
+    if (r != -1000) return r;
+  }
+  return do_env(h, io, 1, nullptr, 0, st);
+}
+
 bool any_obs_output(const gsm_step_io& io) {
   return io.obs || io.nbr_idx || io.nbr_feat || io.nbr_cnt || io.adj || io.assign;
 }
@@ -369,7 +395,7 @@ int gsm_step(gsm_env* h, const gsm_step_io* io, void* stream) {
   if (!h || !io) return GSM_ERR_INVALID_ARG;
   if (!io->actions) return fail(h, GSM_ERR_INVALID_ARG, "io.actions is NULL");
   DeviceGuard guard(h->device);
-  return do_env(h, *io, 1, nullptr, 0, (cudaStream_t)stream);
+  return do_step(h, *io, (cudaStream_t)stream);
 }
 
 int gsm_observe(gsm_env* h, const gsm_step_io* io, void* stream) {
@@ -382,6 +408,10 @@ int gsm_rollout(gsm_env* h, int32_t n_steps, const gsm_step_io* io, void* stream
   if (!h || !io || n_steps < 1) return GSM_ERR_INVALID_ARG;
   if (!io->actions) return fail(h, GSM_ERR_INVALID_ARG, "io.actions is NULL");
   DeviceGuard guard(h->device);
+  if (h->plan.spec) {               // fused: all n_steps in one launch, state stays in registers
+    const int r = do_steps(h, *io, n_steps, (cudaStream_t)stream);
+    if (r != -1000) return r;
+  }
   const bool hit = h->graph_exec && h->graph_steps == n_steps &&
                    std::memcmp(&h->graph_io, io, sizeof(gsm_step_io)) == 0;
   if (!hit) {
@@ -395,7 +425,7 @@ int gsm_rollout(gsm_env* h, int32_t n_steps, const gsm_step_io* io, void* stream
         unsigned char* b = (unsigned char*)io_get(*io, k);
         io_set(cur, k, b ? b + (size_t)s * h->io_bytes[k] : nullptr);
       }
-      st = do_env(h, cur, 1, nullptr, 0, h->stream);
+      st = do_step(h, cur, h->stream);
     }
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
@@ -475,7 +505,7 @@ int gsm_step_host(gsm_env* h, const gsm_step_io* io) {
   if (st) return st;
   GSM_CUDA(h, cudaMemcpyAsync(const_cast<void*>(h->d_io.actions), io->actions, h->io_bytes[IO_ACTIONS],
                               cudaMemcpyHostToDevice, h->stream));
-  st = do_env(h, h->d_io, 1, nullptr, 0, h->stream);
+  st = do_step(h, h->d_io, h->stream);
   if (st) return st;
   return copy_out(h, *io, true);
 }

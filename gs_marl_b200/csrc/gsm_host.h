@@ -22,6 +22,10 @@ struct HostParams {
   void* agent_state; void* lm_pos; int32_t* t; int32_t* episode;
 };
 
+struct RolloutStrides {  // bytes between consecutive steps of each rollout buffer
+  int64_t actions, obs, nbr_idx, nbr_feat, nbr_cnt, adj, reward, cost, done, assign;
+};
+
 struct LaunchPlan {     // chosen once per handle
   int cta_env;          // 1: one env per CTA; 0: packed envs per warp
   int P;                // lanes per agent
@@ -29,6 +33,7 @@ struct LaunchPlan {     // chosen once per handle
   int envs_per_cta;
   size_t smem;
   int64_t grid;
+  int spec;             // 1: a size-specialised register-resident kernel exists (gsm_kernels_spec.cuh)
 };
 
 // Each returns a cudaError_t (as int).  physics: 1 = full step, 0 = observe only.
@@ -38,6 +43,12 @@ int launch_env_f32(const HostParams& hp, const LaunchPlan& plan, const gsm_step_
                    const uint8_t* mask, int64_t mask_stride, cudaStream_t st);
 int launch_env_f64(const HostParams& hp, const LaunchPlan& plan, const gsm_step_io& io, int physics,
                    const uint8_t* mask, int64_t mask_stride, cudaStream_t st);
+// n_steps consecutive steps in ONE launch of the specialised kernel; returns -1 if the
+// handle's (scenario, N, L) has no compiled instance.
+int launch_spec_f32(const HostParams& hp, const gsm_step_io& io, int n_steps,
+                    const RolloutStrides& rs, cudaStream_t st);
+int launch_spec_f64(const HostParams& hp, const gsm_step_io& io, int n_steps,
+                    const RolloutStrides& rs, cudaStream_t st);
 int launch_reset_f32(const HostParams& hp, uint64_t seed, const uint8_t* mask, int64_t mask_stride,
                      cudaStream_t st);
 int launch_reset_f64(const HostParams& hp, uint64_t seed, const uint8_t* mask, int64_t mask_stride,

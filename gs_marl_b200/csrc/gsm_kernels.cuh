@@ -53,26 +53,28 @@ struct KParams {
 
 // ---- shared-memory carve-up (same arithmetic on host and device) ---------------------
 struct SmemLayout {
-  int epb;        // envs per CTA
-  int lsa;        // scenario needs the assignment scratch
-  size_t off_size, off_ag, off_lm, off_new, off_tgt, off_rew, off_slot, off_cmat, off_asg,
-      off_flag, total;
+  size_t off_size, off_agc, off_ag, off_lm, off_new, off_rew, off_slot, off_cmat, off_asg,
+      off_stage, off_flag, stage_stride, stage_feat, total;
 };
-__host__ __device__ inline SmemLayout make_layout(int rb, int N, int L, int E, int epb, int lsa) {
+// epb: envs per CTA; groups: agent groups per CTA (kThreads / P); K: padded neighbour rows.
+__host__ __device__ inline SmemLayout make_layout(int rb, int N, int L, int E, int K, int epb,
+                                                  int groups, int lsa) {
   SmemLayout s;
-  s.epb = epb; s.lsa = lsa;
   size_t o = 0;
-  auto take = [&](size_t n_real) { size_t r = o; o += ((n_real * rb + 15) / 16) * 16; return r; };
-  s.off_size = take(E);
-  s.off_ag = take((size_t)epb * N * 4);
-  s.off_lm = take((size_t)epb * L * 2);
-  s.off_new = take((size_t)epb * N * 4);
-  s.off_tgt = take((size_t)epb * N * 2);
-  s.off_rew = take((size_t)epb * N);
-  s.off_slot = take(lsa ? (size_t)epb * N * 2 : 0);
-  s.off_cmat = take(lsa ? (size_t)epb * N * N : 0);
-  s.off_asg = o; o += (((size_t)epb * N * 4 + 15) / 16) * 16;
-  s.off_flag = o; o += (((size_t)E + 15) / 16) * 16;
+  auto take = [&](size_t bytes) { size_t r = o; o += ((bytes + 15) / 16) * 16; return r; };
+  s.off_size = take((size_t)E * rb);
+  s.off_agc = take((size_t)N * 3 * rb);                  // mass, accel, max_speed
+  s.off_ag = take((size_t)epb * N * 4 * rb);
+  s.off_lm = take((size_t)epb * L * 2 * rb);
+  s.off_new = take((size_t)epb * N * 4 * rb);
+  s.off_rew = take((size_t)epb * N * rb);
+  s.off_slot = take(lsa ? (size_t)epb * N * 2 * rb : 0);
+  s.off_cmat = take(lsa ? (size_t)epb * N * N * rb : 0);
+  s.off_asg = take((size_t)epb * N * 4);
+  s.stage_feat = (((size_t)K * 4 + 15) / 16) * 16;       // idx rows first, then feat rows
+  s.stage_stride = s.stage_feat + (((size_t)K * GSM_NBR_FEAT_DIM * rb + 15) / 16) * 16;
+  s.off_stage = take((size_t)groups * s.stage_stride);
+  s.off_flag = take((size_t)E);
   s.total = o;
   return s;
 }
@@ -118,6 +120,27 @@ template <typename T> __device__ __forceinline__ T r_inf();
 template <> __device__ __forceinline__ float r_inf<float>() { return __int_as_float(0x7f800000); }
 template <> __device__ __forceinline__ double r_inf<double>() {
   return __longlong_as_double(0x7ff0000000000000ll);
+}
+
+// Production precision may drop contact terms that cannot change an fp32 result: for
+// x = -(dist - dmin)/margin < -kFarCut the penetration is < margin * 2.1e-9 (SPEC §3 note).
+template <typename T> struct Prec;
+template <> struct Prec<float> { static constexpr bool kCut = true; };
+template <> struct Prec<double> { static constexpr bool kCut = false; };
+constexpr float kFarCut = 20.0f;
+
+// Cooperative copy of `bytes` (multiple of 4) from shared to global by the P lanes of a
+// group, with the widest vector both addresses allow.
+template <int P>
+__device__ __forceinline__ void group_copy(void* gdst, const void* ssrc, int bytes, int sub) {
+  const uintptr_t ga = (uintptr_t)gdst;
+  if (((ga | (uintptr_t)bytes) & 15) == 0) {
+    for (int k = sub; k < (bytes >> 4); k += P) ((int4*)gdst)[k] = ((const int4*)ssrc)[k];
+  } else if (((ga | (uintptr_t)bytes) & 7) == 0) {
+    for (int k = sub; k < (bytes >> 3); k += P) ((int2*)gdst)[k] = ((const int2*)ssrc)[k];
+  } else {
+    for (int k = sub; k < (bytes >> 2); k += P) ((int*)gdst)[k] = ((const int*)ssrc)[k];
+  }
 }
 
 // SPEC §5.  scipy rectangular_lsap (Crouse 2016) on an n x n matrix in shared memory,
@@ -181,18 +204,21 @@ __device__ int lsa_lanes(const T* __restrict__ C, int n, int col, unsigned gm, i
 }
 
 // ---- the fused env kernel ------------------------------------------------------------
+// Lane roles: an agent is served by a group of P lanes; lane `sub` of the group handles the
+// "other" entities o = sub, sub+P, ... (o indexes the E-1 entities != i), so for P >= E-1
+// (navigation N=3: E-1 = 8 = P) every pair is one lane and the pair loops run once.
 template <typename T, int P, bool CTA_ENV, bool PHYS>
 __global__ void __launch_bounds__(kThreads) env_kernel(const __grid_constant__ KParams<T> p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int N = p.N, L = p.L, E = p.E, K = p.K, W = p.W;
   const bool lsa = p.scenario != GSM_SCN_NAVIGATION;
   const int EPB = CTA_ENV ? 1 : p.envs_per_warp * (kThreads / 32);
-  const SmemLayout lay = make_layout((int)sizeof(T), N, L, E, EPB, lsa ? 1 : 0);
+  const SmemLayout lay = make_layout((int)sizeof(T), N, L, E, K, EPB, kThreads / P, lsa ? 1 : 0);
   T* s_size = (T*)(smem + lay.off_size);
+  T* s_agc = (T*)(smem + lay.off_agc);
   T* s_ag = (T*)(smem + lay.off_ag);
   T* s_lm = (T*)(smem + lay.off_lm);
   T* s_new = (T*)(smem + lay.off_new);
-  T* s_tgt = (T*)(smem + lay.off_tgt);
   T* s_rew = (T*)(smem + lay.off_rew);
   T* s_slot = (T*)(smem + lay.off_slot);
   T* s_cmat = (T*)(smem + lay.off_cmat);
@@ -201,6 +227,9 @@ __global__ void __launch_bounds__(kThreads) env_kernel(const __grid_constant__ K
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int e = tid; e < E; e += kThreads) { s_size[e] = p.size[e]; s_flag[e] = p.eflag[e]; }
+  for (int i = tid; i < N; i += kThreads) {
+    s_agc[3 * i] = p.mass[i]; s_agc[3 * i + 1] = p.accel[i]; s_agc[3 * i + 2] = p.max_speed[i];
+  }
 
   // ---- mapping -----------------------------------------------------------------------
   int env_l;          // env slot inside the CTA
@@ -228,10 +257,12 @@ __global__ void __launch_bounds__(kThreads) env_kernel(const __grid_constant__ K
     if (!active) { first_agent = N; env_l = 0; }
   }
   if (p.mask != nullptr && active && p.mask[env * p.mask_stride] == 0) {
-    // observe-after-reset on a subset: in packed mode the whole env group drops out
-    // together (the predicate is per env); in cta-env mode the whole CTA does.
+    // observe-after-reset on a subset: the whole env group (packed) / CTA (cta-env) drops out
     active = false; first_agent = N;
   }
+  unsigned char* stage = smem + lay.off_stage + (size_t)(tid / P) * lay.stage_stride;
+  int32_t* st_idx = (int32_t*)stage;
+  T* st_feat = (T*)(stage + lay.stage_feat);
 
   // ---- stage state: coalesced, contiguous per warp (packed) / per CTA (cta-env) --------
   if (CTA_ENV) {
@@ -256,7 +287,6 @@ __global__ void __launch_bounds__(kThreads) env_kernel(const __grid_constant__ K
   const T* e_ag = s_ag + (size_t)env_l * N * 4;
   const T* e_lm = s_lm + (size_t)env_l * L * 2;
   T* e_new = s_new + (size_t)env_l * N * 4;
-  T* e_tgt = s_tgt + (size_t)env_l * N * 2;
   T* e_rew = s_rew + (size_t)env_l * N;
   int t_now = 0;
   if (active) t_now = p.t[env] + (PHYS ? 1 : 0);
@@ -275,13 +305,14 @@ __global__ void __launch_bounds__(kThreads) env_kernel(const __grid_constant__ K
           const T* ap = (const T*)p.actions + (env * N + i) * 2;
           ux = ap[0]; uy = ap[1];
         }
-        const T acc = p.accel[i];
+        const T acc = s_agc[3 * i + 1];
         fx = acc * ux; fy = acc * uy;
       }
       if (s_flag[i] & 1) {
         const T si = s_size[i];
-        for (int j = sub; j < E; j += P) {
-          if (j == i || !(s_flag[j] & 1)) continue;
+        for (int o = sub; o < E - 1; o += P) {
+          const int j = o + (o >= i ? 1 : 0);
+          if (!(s_flag[j] & 1)) continue;
           T qx, qy;
           if (j < N) { qx = e_ag[4 * j]; qy = e_ag[4 * j + 1]; }
           else { qx = e_lm[2 * (j - N)]; qy = e_lm[2 * (j - N) + 1]; }
@@ -289,6 +320,7 @@ __global__ void __launch_bounds__(kThreads) env_kernel(const __grid_constant__ K
           const T dist = r_sqrt(dx * dx + dy * dy);
           const T dmin = si + s_size[j];
           const T x = -(dist - dmin) / p.km;
+          if (Prec<T>::kCut && x < (T)(-kFarCut)) continue;
           const T pen = softplus(x) * p.km;
           fx = fx + p.cf * dx / dist * pen;
           fy = fy + p.cf * dy / dist * pen;
@@ -303,10 +335,10 @@ __global__ void __launch_bounds__(kThreads) env_kernel(const __grid_constant__ K
       }
       if (sub == 0) {
         T vx = e_ag[4 * i + 2] * p.one_minus_damp, vy = e_ag[4 * i + 3] * p.one_minus_damp;
-        const T m = p.mass[i];
+        const T m = s_agc[3 * i];
         vx = vx + (fx / m) * p.dt;
         vy = vy + (fy / m) * p.dt;
-        const T ms = p.max_speed[i];
+        const T ms = s_agc[3 * i + 2];
         if (ms > (T)0) {
           const T sp = r_sqrt(vx * vx + vy * vy);
           if (sp > ms) { vx = vx / sp * ms; vy = vy / sp * ms; }
@@ -370,19 +402,13 @@ __global__ void __launch_bounds__(kThreads) env_kernel(const __grid_constant__ K
     const T px = cur[4 * i], py = cur[4 * i + 1], vx = cur[4 * i + 2], vy = cur[4 * i + 3];
     const int64_t row = env * N + i;
     const T si = s_size[i];
-    T tx, ty;
-    int asg = i;
-    if (lsa) {
-      asg = s_asg[(size_t)env_l * N + i];
-      tx = s_slot[((size_t)env_l * N + asg) * 2]; ty = s_slot[((size_t)env_l * N + asg) * 2 + 1];
-    } else {
-      tx = e_lm[2 * i]; ty = e_lm[2 * i + 1];
-    }
     int cnt = 0, ncol = 0;
-    uint32_t word = 0;
-    for (int e0 = 0; e0 < E; e0 += P) {
-      const int e = e0 + sub;
-      const bool valid = e < E && e != i;
+    uint32_t word = 0;      // adjacency word under construction (lane sub == 0 keeps it)
+    int wcur = 0;
+    for (int o0 = 0; o0 < E - 1; o0 += P) {
+      const int o = o0 + sub;
+      const bool valid = o < E - 1;
+      const int e = o + (o >= i ? 1 : 0);
       T dx = 0, dy = 0, dvx = 0, dvy = 0, dist = 0;
       bool nb = false, col = false;
       int fl = 0;
@@ -398,40 +424,65 @@ __global__ void __launch_bounds__(kThreads) env_kernel(const __grid_constant__ K
         if (dist < si + s_size[e])
           col = (e < N) || (p.cost_obstacles && (fl >> 1) == GSM_ENT_OBSTACLE);
       }
+      // neighbour compaction: ballot + popc prefix inside the group
       unsigned bits, cbits;
       if (P == 1) { bits = nb ? 1u : 0u; cbits = col ? 1u : 0u; }
       else {
         const int sh = (lane - sub) & 31;
-        bits = __ballot_sync(grpmask, nb) >> sh;
-        cbits = __ballot_sync(grpmask, col) >> sh;
-        bits &= low_mask(P); cbits &= low_mask(P);
+        bits = (__ballot_sync(grpmask, nb) >> sh) & low_mask(P);
+        cbits = (__ballot_sync(grpmask, col) >> sh) & low_mask(P);
       }
-      const int pos = cnt + __popc(bits & ((1u << sub) - 1u));
+      const int pos = cnt + __popc(bits & low_mask(sub));
       if (nb && pos < K) {
-        if (p.nbr_idx) p.nbr_idx[row * K + pos] = e;
-        if (p.nbr_feat) {
-          T* f = p.nbr_feat + (row * K + pos) * GSM_NBR_FEAT_DIM;
-          f[0] = dx; f[1] = dy; f[2] = dvx; f[3] = dvy; f[4] = dist; f[5] = (T)(fl >> 1);
-        }
+        st_idx[pos] = e;
+        T* f = st_feat + pos * GSM_NBR_FEAT_DIM;
+        f[0] = dx; f[1] = dy; f[2] = dvx; f[3] = dvy; f[4] = dist; f[5] = (T)(fl >> 1);
       }
       cnt += __popc(bits);
       ncol += __popc(cbits);
-      word |= bits << (e0 & 31);
-      if (((e0 + P) & 31) == 0 || e0 + P >= E) {
-        if (sub == 0 && p.adj) p.adj[row * W + (e0 >> 5)] = word;
-        word = 0;
+      // adjacency words: a chunk's entity indices e_lo..e_hi are contiguous (self skipped),
+      // ascending from chunk to chunk, and touch at most two 32-bit words.
+      const int o_hi = (o0 + P - 1 < E - 2) ? o0 + P - 1 : E - 2;
+      const int e_lo = o0 + (o0 >= i ? 1 : 0), e_hi = o_hi + (o_hi >= i ? 1 : 0);
+      const int w_lo = e_lo >> 5, w_hi = e_hi >> 5;
+      uint32_t c0 = (nb && (e >> 5) == w_lo) ? (1u << (e & 31)) : 0u;
+      uint32_t c1 = (nb && (e >> 5) != w_lo) ? (1u << (e & 31)) : 0u;
+      if (P > 1) { c0 = __reduce_or_sync(grpmask, c0); c1 = __reduce_or_sync(grpmask, c1); }
+      if (w_lo != wcur) {
+        if (sub == 0 && p.adj) p.adj[row * W + wcur] = word;
+        word = 0; wcur = w_lo;
       }
+      word |= c0;
+      if (w_hi != w_lo) {
+        if (sub == 0 && p.adj) p.adj[row * W + wcur] = word;
+        word = c1; wcur = w_hi;
+      }
+    }
+    if (sub == 0 && p.adj) {
+      p.adj[row * W + wcur] = word;
+      for (int w = wcur + 1; w < W; w++) p.adj[row * W + w] = 0u;
     }
     if (cnt > K) cnt = K;
     for (int k = cnt + sub; k < K; k += P) {
-      if (p.nbr_idx) p.nbr_idx[row * K + k] = -1;
-      if (p.nbr_feat) {
-        T* f = p.nbr_feat + (row * K + k) * GSM_NBR_FEAT_DIM;
+      st_idx[k] = -1;
+      T* f = st_feat + k * GSM_NBR_FEAT_DIM;
 #pragma unroll
-        for (int q = 0; q < GSM_NBR_FEAT_DIM; q++) f[q] = 0;
-      }
+      for (int q = 0; q < GSM_NBR_FEAT_DIM; q++) f[q] = 0;
     }
+    if (P > 1) __syncwarp(grpmask);
+    if (p.nbr_idx) group_copy<P>(p.nbr_idx + row * K, st_idx, K * 4, sub);
+    if (p.nbr_feat)
+      group_copy<P>(p.nbr_feat + row * K * GSM_NBR_FEAT_DIM, st_feat, K * GSM_NBR_FEAT_DIM * (int)sizeof(T), sub);
+    if (P > 1) __syncwarp(grpmask);          // staging is reused by the group's next agent
     if (sub == 0) {
+      T tx, ty;
+      int asg = i;
+      if (lsa) {
+        asg = s_asg[(size_t)env_l * N + i];
+        tx = s_slot[((size_t)env_l * N + asg) * 2]; ty = s_slot[((size_t)env_l * N + asg) * 2 + 1];
+      } else {
+        tx = e_lm[2 * i]; ty = e_lm[2 * i + 1];
+      }
       if (p.nbr_cnt) p.nbr_cnt[row] = cnt;
       if (p.assign) p.assign[row] = asg;
       const T gx = tx - px, gy = ty - py;

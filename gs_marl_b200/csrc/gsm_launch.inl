@@ -10,26 +10,18 @@ static int env_int(const char* name, int dflt) {
   return v ? std::atoi(v) : dflt;
 }
 
-// Lane efficiency of the packed mapping with P lanes per agent.
-static double packed_eff(int N, int E, int P) {
-  const int lpe = N * P;
-  if (lpe > 32) return 0.0;
-  const int epw = 32 / lpe;
-  const int iters = (E + P - 1) / P;
-  return ((double)E / (double)(P * iters)) * ((double)(epw * lpe) / 32.0);
-}
+static bool has_spec(const HostParams& hp);
+static int next_pow2(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
 int GSM_SFX(plan)(const HostParams& hp, LaunchPlan* plan) {
   const int N = hp.N, E = hp.N + hp.L;
   const bool lsa = hp.scenario != GSM_SCN_NAVIGATION;
+  // One lane per (agent, other entity) pair where a warp can hold an env: P = min(32/N,
+  // next_pow2(E-1)).  Larger teams get one CTA per env with a warp per agent.
   int cta_env, P;
-  if (N <= 32) {
+  if (N <= 12) {
     cta_env = 0; P = 1;
-    double best = packed_eff(N, E, 1);
-    for (int q = 2; q <= 4; q *= 2) {
-      const double e = packed_eff(N, E, q);
-      if (e >= best - 1e-9 && e > 0) { best = e; P = q; }
-    }
+    while (N * P * 2 <= 32 && P * 2 <= next_pow2(E - 1 > 1 ? E - 1 : 1)) P *= 2;
   } else {
     cta_env = 1; P = 32;
   }
@@ -43,10 +35,12 @@ int GSM_SFX(plan)(const HostParams& hp, LaunchPlan* plan) {
   plan->P = P;
   plan->envs_per_warp = cta_env ? 0 : 32 / (N * P);
   plan->envs_per_cta = cta_env ? 1 : plan->envs_per_warp * (kThreads / 32);
-  const SmemLayout lay = make_layout((int)sizeof(GSM_REAL), N, hp.L, E, plan->envs_per_cta, lsa ? 1 : 0);
+  const SmemLayout lay = make_layout((int)sizeof(GSM_REAL), N, hp.L, E, hp.K, plan->envs_per_cta,
+                                     kThreads / P, lsa ? 1 : 0);
   plan->smem = lay.total;
   plan->grid = (hp.n_envs + plan->envs_per_cta - 1) / plan->envs_per_cta;
   if (plan->smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+  plan->spec = has_spec(hp) ? 1 : 0;
   return 0;
 }
 
@@ -66,11 +60,9 @@ static int launch_phys(const KParams<GSM_REAL>& kp, const LaunchPlan& plan, int 
   return physics ? launch_one<P, CTA_ENV, true>(kp, plan, st) : launch_one<P, CTA_ENV, false>(kp, plan, st);
 }
 
-int GSM_SFX(launch_env)(const HostParams& hp, const LaunchPlan& plan, const gsm_step_io& io,
-                        int physics, const uint8_t* mask, int64_t mask_stride, cudaStream_t st) {
+static void fill_kparams(KParams<GSM_REAL>& kp, const HostParams& hp, const gsm_step_io& io,
+                         int envs_per_warp, const uint8_t* mask, int64_t mask_stride) {
   typedef GSM_REAL T;
-  if (hp.n_envs == 0) return 0;
-  KParams<T> kp;
   std::memset(&kp, 0, sizeof(kp));
   kp.n_envs = hp.n_envs; kp.env_offset = hp.env_offset;
   kp.N = hp.N; kp.L = hp.L; kp.E = hp.N + hp.L; kp.K = hp.K; kp.W = (kp.E + 31) / 32;
@@ -78,7 +70,7 @@ int GSM_SFX(launch_env)(const HostParams& hp, const LaunchPlan& plan, const gsm_
   kp.episode_length = hp.episode_length;
   kp.share_reward = hp.share_reward; kp.cost_obstacles = hp.cost_obstacles;
   kp.own_goal_always = hp.own_goal_always;
-  kp.envs_per_warp = plan.envs_per_warp;
+  kp.envs_per_warp = envs_per_warp;
   kp.dt = (T)hp.dt; kp.one_minus_damp = (T)1 - (T)hp.damping;
   kp.cf = (T)hp.cf; kp.km = (T)hp.km; kp.Rs = (T)hp.Rs;
   kp.w_dist = (T)hp.w_dist; kp.w_goal = (T)hp.w_goal; kp.goal_tol = (T)hp.goal_tol;
@@ -96,6 +88,13 @@ int GSM_SFX(launch_env)(const HostParams& hp, const LaunchPlan& plan, const gsm_
   kp.obs = (T*)io.obs; kp.nbr_idx = io.nbr_idx; kp.nbr_feat = (T*)io.nbr_feat;
   kp.nbr_cnt = io.nbr_cnt; kp.adj = io.adj; kp.reward = (T*)io.reward; kp.cost = (T*)io.cost;
   kp.done = io.done; kp.assign = io.assign;
+}
+
+int GSM_SFX(launch_env)(const HostParams& hp, const LaunchPlan& plan, const gsm_step_io& io,
+                        int physics, const uint8_t* mask, int64_t mask_stride, cudaStream_t st) {
+  if (hp.n_envs == 0) return 0;
+  KParams<GSM_REAL> kp;
+  fill_kparams(kp, hp, io, plan.envs_per_warp, mask, mask_stride);
   if (plan.cta_env) {
     switch (plan.P) {
       case 1: return launch_phys<1, true>(kp, plan, physics, st);
@@ -114,6 +113,56 @@ int GSM_SFX(launch_env)(const HostParams& hp, const LaunchPlan& plan, const gsm_
     case 16: return launch_phys<16, false>(kp, plan, physics, st);
     default: return launch_phys<32, false>(kp, plan, physics, st);
   }
+}
+
+// ---- size-specialised instances (gsm_kernels_spec.cuh) ------------------------------------
+// (scenario, N, L, P): P = lanes per agent, chosen so that N*P <= 32 and P covers as many of
+// the E-1 "other" entities per pass as a warp allows.
+#define GSM_SPEC_TABLE(X)                                                              \
+  X(GSM_SCN_NAVIGATION, 3, 6, 8) X(GSM_SCN_NAVIGATION, 6, 12, 4) X(GSM_SCN_NAVIGATION, 12, 24, 2) \
+  X(GSM_SCN_POLYGON, 3, 1, 4) X(GSM_SCN_POLYGON, 4, 1, 4) X(GSM_SCN_POLYGON, 5, 1, 4)  \
+  X(GSM_SCN_POLYGON, 6, 1, 4) X(GSM_SCN_POLYGON, 12, 1, 2)                             \
+  X(GSM_SCN_LINE, 3, 2, 4) X(GSM_SCN_LINE, 4, 2, 4) X(GSM_SCN_LINE, 5, 2, 4)           \
+  X(GSM_SCN_LINE, 6, 2, 4) X(GSM_SCN_LINE, 12, 2, 2)
+
+static bool spec_enabled() {
+  return env_int("GSM_NO_SPEC", 0) == 0 && env_int("GSM_FORCE_P", 0) == 0 &&
+         env_int("GSM_FORCE_CTA_ENV", -1) < 0;
+}
+
+static bool has_spec(const HostParams& hp) {
+  if (!spec_enabled()) return false;
+#define X(S, n, l, pp) if (hp.scenario == S && hp.N == n && hp.L == l) return true;
+  GSM_SPEC_TABLE(X)
+#undef X
+  return false;
+}
+
+template <int SCN, int N, int L, int P>
+static int launch_spec_one(const KParams<GSM_REAL>& kp, int n_steps, const StepStrides& ss,
+                           cudaStream_t st) {
+  constexpr int EPW = 32 / (N * P), WPC = kSpecThreads / 32;
+  const int64_t grid = (kp.n_envs + EPW * WPC - 1) / (EPW * WPC);
+  const size_t smem = SCN == GSM_SCN_NAVIGATION ? 0 : (size_t)WPC * EPW * N * N * sizeof(GSM_REAL);
+  env_steps_kernel<GSM_REAL, SCN, N, L, P><<<(unsigned)grid, kSpecThreads, smem, st>>>(kp, n_steps, ss);
+  return (int)cudaGetLastError();
+}
+
+int GSM_SFX(launch_spec)(const HostParams& hp, const gsm_step_io& io, int n_steps,
+                         const RolloutStrides& rs, cudaStream_t st) {
+  if (!has_spec(hp)) return -1;
+  if (hp.n_envs == 0) return 0;
+  KParams<GSM_REAL> kp;
+  fill_kparams(kp, hp, io, 0, nullptr, 0);
+  StepStrides ss;
+  ss.actions = rs.actions; ss.obs = rs.obs; ss.nbr_idx = rs.nbr_idx; ss.nbr_feat = rs.nbr_feat;
+  ss.nbr_cnt = rs.nbr_cnt; ss.adj = rs.adj; ss.reward = rs.reward; ss.cost = rs.cost;
+  ss.done = rs.done; ss.assign = rs.assign;
+#define X(S, n, l, pp) \
+  if (hp.scenario == S && hp.N == n && hp.L == l) return launch_spec_one<S, n, l, pp>(kp, n_steps, ss, st);
+  GSM_SPEC_TABLE(X)
+#undef X
+  return -1;
 }
 
 int GSM_SFX(launch_reset)(const HostParams& hp, uint64_t seed, const uint8_t* mask,

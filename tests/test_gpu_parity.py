@@ -43,7 +43,7 @@ def _squeezed_start(cfg, n, seed, scale=0.45):
     return o
 
 
-@pytest.fixture(params=[None, 1, 2, 4, "cta32", "cta8"])
+@pytest.fixture(params=[None, 1, 2, 4, 8, "cta32", "cta8"])
 def mapping(request, monkeypatch):
     """Every thread mapping of the env kernel must give the same answers."""
     m = request.param
