@@ -176,6 +176,8 @@ int do_env(gsm_env* h, const gsm_step_io& io, int physics, const uint8_t* mask, 
 
 // One env step (physics + outputs): the size-specialised kernel when the handle has one.
 int do_steps(gsm_env* h, const gsm_step_io& io, int n_steps, cudaStream_t st) {
+  for (int k = IO_OBS; k < IO_COUNT; k++)
+    if (!io_get(io, k)) return -1000;   // the specialised kernel writes every output
   gsm::RolloutStrides rs;
   std::memset(&rs, 0, sizeof(rs));
   if (n_steps > 1) {

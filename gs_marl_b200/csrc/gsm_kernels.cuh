@@ -33,7 +33,7 @@ struct KParams {
   int scenario, action_mode, n_actions, episode_length;
   int share_reward, cost_obstacles, own_goal_always;
   int envs_per_warp;  // packed mode
-  T dt, one_minus_damp, cf, km, Rs, w_dist, w_goal, goal_tol, poly_r;
+  T dt, one_minus_damp, cf, km, km_inv, Rs, w_dist, w_goal, goal_tol, poly_r;
   T discrete_u[GSM_MAX_DISCRETE][2];
   const T* size;           // [E]
   const uint8_t* eflag;    // [E] bit0 collide, bits1..2 type

@@ -8,7 +8,7 @@
 //   * the pair force is reduced with xor-shuffles, the integration is done redundantly by
 //     the P lanes of the agent (no broadcast, no divergence),
 //   * neighbour rows are compacted with ballot+popc and written straight to HBM, the
-//     adjacency word comes from redux.or,
+//     adjacency word is assembled from the ballot bits,
 //   * no shared memory and no block barrier on the navigation path (polygon/line keep the
 //     N x N assignment matrix in shared memory for the in-warp LSA).
 // With n_steps > 1 this is the fused rollout kernel: per step it only reads the actions
@@ -23,9 +23,6 @@ constexpr int kSpecThreads = 128;
 template <typename T> struct Vec2;
 template <> struct Vec2<float> { typedef float2 type; };
 template <> struct Vec2<double> { typedef double2 type; };
-template <typename T> struct Vec4;
-template <> struct Vec4<float> { typedef float4 type; };
-template <> struct Vec4<double> { typedef double4 type; };
 
 template <typename T>
 __device__ __forceinline__ void st2(T* p, T a, T b) {
@@ -33,11 +30,34 @@ __device__ __forceinline__ void st2(T* p, T a, T b) {
   *reinterpret_cast<typename Vec2<T>::type*>(p) = v;
 }
 
+// Arithmetic policy.  fp64 (verification): exactly the operations SPEC.md writes.  fp32
+// (production, 1e-4 relative): reciprocal-multiply for the two constant divisors and the
+// approximate SFU sqrt / divide (<= 2 ulp) — no IEEE slow paths in the step loop.
+template <typename T> struct Arith;
+template <> struct Arith<double> {
+  static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+  static __device__ __forceinline__ double div(double a, double b) { return a / b; }
+  static __device__ __forceinline__ double div_const(double a, double b, double /*b_inv*/) { return a / b; }
+};
+template <> struct Arith<float> {
+  static __device__ __forceinline__ float sqrt(float x) {
+    float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+  }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+  static __device__ __forceinline__ float div_const(float a, float /*b*/, float b_inv) { return a * b_inv; }
+};
+
 // Per-step byte strides of the rollout buffers (0 for single-step use).
 struct StepStrides {
   int64_t actions, obs, nbr_idx, nbr_feat, nbr_cnt, adj, reward, cost, done, assign;
 };
 
+template <int E> struct AdjBits { typedef uint64_t type; };
+template <> struct AdjBits<0> { typedef uint32_t type; };
+
+// Every output pointer must be non-NULL (the API layer falls back to the generic kernel
+// otherwise).  All 32 lanes stay alive and use FULL-mask warp primitives: lanes without a
+// real env compute on a clamped env index and only their stores are predicated off.
 template <typename T, int SCN, int N, int L, int P>
 __global__ void __launch_bounds__(kSpecThreads)
 env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
@@ -46,47 +66,57 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   constexpr int CH = (M + P - 1) / P;              // chunks of "others" per lane
   constexpr int W = (E + 31) / 32;
   constexpr bool LSA = SCN != GSM_SCN_NAVIGATION;
+  constexpr unsigned FULL = 0xffffffffu;
   static_assert(LPE <= 32 && EPW >= 1, "an env must fit in one warp");
-  static_assert(W == 1 || P == 1 || true, "");
+  static_assert(E <= 64, "adjacency is assembled in one 64-bit register");
+  typedef typename AdjBits<(E <= 32 ? 0 : E)>::type adj_t;
+  typedef Arith<T> A;
   const int K = p.K;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int eiw = lane / LPE;                       // compile-time divisor
   const int off = lane - eiw * LPE;
   const int i = off / P, sub = off % P;             // my agent, my lane in its group
-  const int64_t env = ((int64_t)blockIdx.x * (kSpecThreads / 32) + warp) * EPW + eiw;
-  const bool active = eiw < EPW && env < p.n_envs;
+  const int64_t env_raw = ((int64_t)blockIdx.x * (kSpecThreads / 32) + warp) * EPW + eiw;
+  const bool active = eiw < EPW && env_raw < p.n_envs;
+  const int64_t env = active ? env_raw : 0;         // idle lanes shadow env 0, never store
   const int env_base = eiw * LPE;
+  const int grp_base = env_base + i * P;
   const unsigned envmask = low_mask(LPE) << (env_base & 31);
-  const unsigned grpmask = low_mask(P) << ((lane - sub) & 31);
 
   extern __shared__ __align__(16) unsigned char smem_spec[];
   T* s_cm = nullptr;                                // [EPW per warp][N*N] assignment costs
   if (LSA) s_cm = (T*)smem_spec + ((size_t)warp * EPW + (eiw < EPW ? eiw : 0)) * N * N;
 
-  if (!active) return;                              // whole env groups leave together
-
   // ---- per-lane constants of my pairs ---------------------------------------------------
   const T size_i = p.size[i];
   const bool coll_i = p.eflag[i] & 1;
   const T mass_i = p.mass[i], accel_i = p.accel[i], maxsp_i = p.max_speed[i];
-  int e_c[CH];
-  T dmin_c[CH];
-  int fl_c[CH];
+  const T mass_inv = (T)1 / mass_i;
+  int e_c[CH];                                       // entity of my pair in chunk c (-1: none)
+  int src_c[CH];                                     // lane holding that entity if it is an agent
+  T dmin_c[CH], type_c[CH];
+  bool cpair_c[CH], colc_c[CH], valid_c[CH], goal_c[CH];
 #pragma unroll
   for (int c = 0; c < CH; c++) {
     const int o = c * P + sub;
-    const int e = o + (o >= i ? 1 : 0);
-    e_c[c] = e;
     const bool valid = o < M;
-    fl_c[c] = valid ? (int)p.eflag[e] : 0;
+    const int e = o + (o >= i ? 1 : 0);
+    const int fl = valid ? (int)p.eflag[e] : 0;
+    e_c[c] = valid ? e : -1;
+    src_c[c] = env_base + ((valid && e < N) ? e : 0) * P;
     dmin_c[c] = valid ? size_i + p.size[e] : (T)0;
-    if (!valid) e_c[c] = -1;
+    type_c[c] = (T)(fl >> 1);
+    cpair_c[c] = valid && coll_i && (fl & 1);
+    colc_c[c] = valid && (e < N || (p.cost_obstacles && (fl >> 1) == GSM_ENT_OBSTACLE));
+    valid_c[c] = valid;
+    goal_c[c] = valid && !LSA && p.own_goal_always && e == N + i;   // own goal: always a neighbour
   }
+  // lane-role masks for the per-agent scalar stores
+  const uint32_t rm0 = sub == 0 ? ~0u : 0u, rm1 = sub == 1 ? ~0u : 0u, rm2 = sub == 2 ? ~0u : 0u,
+                 rm3 = sub == 3 ? ~0u : 0u, rm4 = sub == 4 ? ~0u : 0u;
 
   // ---- state into registers -----------------------------------------------------------------
-  typedef typename Vec4<T>::type V4;
-  typedef typename Vec2<T>::type V2;
   T px, py, vx, vy;
   {
     const T* a = p.agent_state + (env * N + i) * 4;
@@ -101,84 +131,110 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       lmx[c] = l[0]; lmy[c] = l[1];
     }
   }
-  // navigation target = own goal; polygon/line markers for the slots
-  T m0x = 0, m0y = 0, m1x = 0, m1y = 0;
-  if (L > 0) { const T* l = p.lm_pos + env * L * 2; m0x = l[0]; m0y = l[1]; if (L > 1) { m1x = l[2]; m1y = l[3]; } }
-  T goalx = 0, goaly = 0;
+  T goalx = 0, goaly = 0;                            // navigation: own goal
   if (!LSA) { const T* l = p.lm_pos + (env * L + i) * 2; goalx = l[0]; goaly = l[1]; }
-  T slotx = 0, sloty = 0;                            // LSA: slot `off` (lanes off < N)
+  T slotx = 0, sloty = 0;                            // polygon / line: slot `off` (lanes off < N)
   if (LSA && off < N) {
+    const T* l = p.lm_pos + env * L * 2;
     if (SCN == GSM_SCN_POLYGON) {
-      slotx = m0x + p.poly_r * p.slot_table[2 * off];
-      sloty = m0y + p.poly_r * p.slot_table[2 * off + 1];
+      slotx = l[0] + p.poly_r * p.slot_table[2 * off];
+      sloty = l[1] + p.poly_r * p.slot_table[2 * off + 1];
     } else {
       const T f = p.slot_table[2 * off];
-      slotx = m0x + f * (m1x - m0x);
-      sloty = m0y + f * (m1y - m0y);
+      slotx = l[0] + f * (l[2] - l[0]);
+      sloty = l[1] + f * (l[3] - l[1]);
     }
   }
   int t_now = p.t[env];
 
-  const unsigned char* act_ptr = (const unsigned char*)p.actions;
-  unsigned char* o_obs = (unsigned char*)p.obs;
-  unsigned char* o_idx = (unsigned char*)p.nbr_idx;
-  unsigned char* o_feat = (unsigned char*)p.nbr_feat;
-  unsigned char* o_cnt = (unsigned char*)p.nbr_cnt;
-  unsigned char* o_adj = (unsigned char*)p.adj;
-  unsigned char* o_rew = (unsigned char*)p.reward;
-  unsigned char* o_cost = (unsigned char*)p.cost;
-  unsigned char* o_done = (unsigned char*)p.done;
-  unsigned char* o_asg = (unsigned char*)p.assign;
+  // ---- per-lane output cursors (advanced by the slot strides every step) -----------------------
   const int64_t row = env * N + i;
+  const unsigned char* c_act = (const unsigned char*)p.actions +
+      (p.action_mode == GSM_ACT_DISCRETE ? row * 4 : row * 2 * (int64_t)sizeof(T));
+  unsigned char* c_idx = (unsigned char*)(p.nbr_idx + row * K);
+  unsigned char* c_feat = (unsigned char*)(p.nbr_feat + row * K * GSM_NBR_FEAT_DIM);
+  // obs: lane sub (and sub + P, ...) writes pair `part` of (vx,vy | px,py | gx,gy)
+  unsigned char* c_obs = (unsigned char*)(p.obs + row * GSM_OBS_DIM + 2 * (sub % 3));
+  constexpr int OBS_PASSES = (3 + P - 1) / P;
+  // per-agent scalars.  P >= 8: one output per lane ("roles": 0 cnt, 1 adj word 0, 2 reward,
+  // 3 cost, 4 assign, 5 done) so that a step issues one 32-bit, one real-sized and one byte
+  // store for all six.  P < 8: lane sub == 0 walks six cursors.
+  constexpr bool ROLES = P >= 8 && W == 1;
+  unsigned char* c_role = nullptr;
+  int64_t role_stride = 0;
+  unsigned char *c_cnt = nullptr, *c_adj = nullptr, *c_rew = nullptr, *c_cost = nullptr,
+                *c_asg = nullptr, *c_done = nullptr;
+  if (ROLES) {
+    switch (sub) {
+      case 0: c_role = (unsigned char*)(p.nbr_cnt + row); role_stride = ss.nbr_cnt; break;
+      case 1: c_role = (unsigned char*)(p.adj + row); role_stride = ss.adj; break;
+      case 2: c_role = (unsigned char*)(p.reward + row); role_stride = ss.reward; break;
+      case 3: c_role = (unsigned char*)(p.cost + row); role_stride = ss.cost; break;
+      case 4: c_role = (unsigned char*)(p.assign + row); role_stride = ss.assign; break;
+      case 5: c_role = (unsigned char*)(p.done + row); role_stride = ss.done; break;
+      default: break;
+    }
+  } else {
+    c_cnt = (unsigned char*)(p.nbr_cnt + row); c_adj = (unsigned char*)(p.adj + row * W);
+    c_rew = (unsigned char*)(p.reward + row); c_cost = (unsigned char*)(p.cost + row);
+    c_asg = (unsigned char*)(p.assign + row); c_done = (unsigned char*)(p.done + row);
+  }
+
+  int act_next = 0;
+  T actx_next = 0, acty_next = 0;
+  if (p.action_mode == GSM_ACT_DISCRETE) act_next = *(const int32_t*)c_act;
+  else { actx_next = ((const T*)c_act)[0]; acty_next = ((const T*)c_act)[1]; }
 
   for (int step = 0; step < n_steps; step++) {
-    // ---- SPEC §2: action force (all P lanes of the agent, same address -> one request) ----
+    // ---- SPEC §2: action force; the next step's action is prefetched -------------------------
     T fx = 0, fy = 0;
     {
-      T ux = 0, uy = 0;
+      T ux = actx_next, uy = acty_next;
       if (p.action_mode == GSM_ACT_DISCRETE) {
-        const int a = ((const int32_t*)act_ptr)[row];
+        const int a = act_next;
+        ux = 0; uy = 0;
         if (a >= 0 && a < p.n_actions) { ux = p.discrete_u[a][0]; uy = p.discrete_u[a][1]; }
-      } else {
-        const T* ap = (const T*)act_ptr + row * 2;
-        ux = ap[0]; uy = ap[1];
       }
       if (sub == 0) { fx = accel_i * ux; fy = accel_i * uy; }
+      c_act += ss.actions;
+      if (step + 1 < n_steps) {
+        if (p.action_mode == GSM_ACT_DISCRETE) act_next = *(const int32_t*)c_act;
+        else { actx_next = ((const T*)c_act)[0]; acty_next = ((const T*)c_act)[1]; }
+      }
     }
     // ---- SPEC §3: pair forces ---------------------------------------------------------------
 #pragma unroll
     for (int c = 0; c < CH; c++) {
       T qx = lmx[c], qy = lmy[c];
       if (c * P < N - 1) {                           // this chunk can hold agent pairs
-        const int src = env_base + (e_c[c] >= 0 && e_c[c] < N ? e_c[c] : 0) * P;
-        const T ax = shfl(envmask, px, src), ay = shfl(envmask, py, src);
+        const T ax = shfl(FULL, px, src_c[c]), ay = shfl(FULL, py, src_c[c]);
         if (e_c[c] >= 0 && e_c[c] < N) { qx = ax; qy = ay; }
       }
-      if (coll_i && (fl_c[c] & 1)) {
+      if (cpair_c[c]) {
         const T dx = px - qx, dy = py - qy;
-        const T dist = r_sqrt(dx * dx + dy * dy);
-        const T x = -(dist - dmin_c[c]) / p.km;
+        const T dist = A::sqrt(dx * dx + dy * dy);
+        const T x = A::div_const(-(dist - dmin_c[c]), p.km, p.km_inv);
         if (!(Prec<T>::kCut && x < (T)(-kFarCut))) {
           const T pen = softplus(x) * p.km;
-          fx = fx + p.cf * dx / dist * pen;
-          fy = fy + p.cf * dy / dist * pen;
+          fx = fx + A::div(p.cf * dx, dist) * pen;
+          fy = fy + A::div(p.cf * dy, dist) * pen;
         }
       }
     }
     if (P > 1) {
 #pragma unroll
       for (int m = P / 2; m >= 1; m >>= 1) {
-        fx += __shfl_xor_sync(grpmask, fx, m);
-        fy += __shfl_xor_sync(grpmask, fy, m);
+        fx += __shfl_xor_sync(FULL, fx, m);
+        fy += __shfl_xor_sync(FULL, fy, m);
       }
     }
     // ---- SPEC §4: integration, redundantly on the P lanes of the agent --------------------
     vx = vx * p.one_minus_damp; vy = vy * p.one_minus_damp;
-    vx = vx + (fx / mass_i) * p.dt;
-    vy = vy + (fy / mass_i) * p.dt;
+    vx = vx + A::div_const(fx, mass_i, mass_inv) * p.dt;
+    vy = vy + A::div_const(fy, mass_i, mass_inv) * p.dt;
     if (maxsp_i > (T)0) {
-      const T sp = r_sqrt(vx * vx + vy * vy);
-      if (sp > maxsp_i) { vx = vx / sp * maxsp_i; vy = vy / sp * maxsp_i; }
+      const T sp = A::sqrt(vx * vx + vy * vy);
+      if (sp > maxsp_i) { vx = A::div(vx, sp) * maxsp_i; vy = A::div(vy, sp) * maxsp_i; }
     }
     px = px + vx * p.dt; py = py + vy * p.dt;
     t_now += 1;
@@ -190,120 +246,155 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       // lane off < N is column `off`: cost of every agent row to my slot
 #pragma unroll
       for (int r = 0; r < N; r++) {
-        const T rx = shfl(envmask, px, env_base + r * P), ry = shfl(envmask, py, env_base + r * P);
-        if (off < N) {
+        const T rx = shfl(FULL, px, env_base + r * P), ry = shfl(FULL, py, env_base + r * P);
+        if (off < N && eiw < EPW) {                  // shadow lanes must not touch the matrix
           const T dx = slotx - rx, dy = sloty - ry;
           s_cm[r * N + off] = r_sqrt(dx * dx + dy * dy);
         }
       }
-      __syncwarp(envmask);
-      const int a_row = lsa_lanes<T>(s_cm, N, off, envmask, env_base);   // col4row for row == off
-      __syncwarp(envmask);
-      asg = shfl(envmask, a_row, env_base + i);
-      tx = shfl(envmask, slotx, env_base + asg);
-      ty = shfl(envmask, sloty, env_base + asg);
+      __syncwarp();
+      int a_row = 0;
+      if (eiw < EPW) a_row = lsa_lanes<T>(s_cm, N, off, envmask, env_base);   // col4row, row == off
+      __syncwarp();
+      asg = shfl(FULL, a_row, env_base + i);
+      tx = shfl(FULL, slotx, env_base + asg);
+      ty = shfl(FULL, sloty, env_base + asg);
     }
 
     // ---- SPEC §6: neighbour graph -------------------------------------------------------------
-    int cnt = 0, ncol = 0;
-    uint32_t words[W];
-#pragma unroll
-    for (int w = 0; w < W; w++) words[w] = 0;
-    int32_t* g_idx = (int32_t*)o_idx + row * K;
-    T* g_feat = (T*)o_feat + row * K * GSM_NBR_FEAT_DIM;
+    // Every (lane, chunk) pair owns exactly one of the K output rows: neighbours take rows
+    // [0, cnt) in entity order (ballot + popc), non-neighbours the zero rows behind them —
+    // no separate padding pass.  TWO_PASS keeps the pair features in registers between the
+    // ballot sweep and the row writes (small CH); otherwise rows are written as found and
+    // the padding is a short loop.
+    constexpr bool TWO_PASS = CH <= 4;
+    int ncol = 0;
+    adj_t obits = 0;                                  // neighbour bits over "others" index o
+    T g_dx[TWO_PASS ? CH : 1], g_dy[TWO_PASS ? CH : 1], g_dvx[TWO_PASS ? CH : 1],
+      g_dvy[TWO_PASS ? CH : 1], g_d[TWO_PASS ? CH : 1];
+    int cnt_run = 0;
 #pragma unroll
     for (int c = 0; c < CH; c++) {
       T ex = lmx[c], ey = lmy[c], evx = 0, evy = 0;
       if (c * P < N - 1) {
-        const int src = env_base + (e_c[c] >= 0 && e_c[c] < N ? e_c[c] : 0) * P;
-        const T ax = shfl(envmask, px, src), ay = shfl(envmask, py, src);
-        const T bx = shfl(envmask, vx, src), by = shfl(envmask, vy, src);
+        const T ax = shfl(FULL, px, src_c[c]), ay = shfl(FULL, py, src_c[c]);
+        const T bx = shfl(FULL, vx, src_c[c]), by = shfl(FULL, vy, src_c[c]);
         if (e_c[c] >= 0 && e_c[c] < N) { ex = ax; ey = ay; evx = bx; evy = by; }
       }
-      const int e = e_c[c];
       const T dx = ex - px, dy = ey - py;
-      const T dist = r_sqrt(dx * dx + dy * dy);
-      bool nb = e >= 0 && dist < p.Rs;
-      if (!LSA && p.own_goal_always && e == N + i) nb = true;
-      const bool col = e >= 0 && dist < dmin_c[c] &&
-                       (e < N || (p.cost_obstacles && (fl_c[c] >> 1) == GSM_ENT_OBSTACLE));
+      const T dist = A::sqrt(dx * dx + dy * dy);
+      const bool nb = (valid_c[c] && dist < p.Rs) || goal_c[c];
+      const bool col = colc_c[c] && dist < dmin_c[c];
       unsigned bits, cbits;
       if (P == 1) { bits = nb ? 1u : 0u; cbits = col ? 1u : 0u; }
       else {
-        const int sh = (lane - sub) & 31;
-        bits = (__ballot_sync(grpmask, nb) >> sh) & low_mask(P);
-        cbits = (__ballot_sync(grpmask, col) >> sh) & low_mask(P);
+        bits = (__ballot_sync(FULL, nb) >> grp_base) & low_mask(P);
+        cbits = (__ballot_sync(FULL, col) >> grp_base) & low_mask(P);
       }
-      const int pos = cnt + __popc(bits & low_mask(sub));
-      if (nb && pos < K) {
-        if (o_idx) g_idx[pos] = e;
-        if (o_feat) {
-          T* f = g_feat + pos * GSM_NBR_FEAT_DIM;
-          st2<T>(f, dx, dy); st2<T>(f + 2, evx - vx, evy - vy); st2<T>(f + 4, dist, (T)(fl_c[c] >> 1));
-        }
-      }
-      cnt += __popc(bits);
       ncol += __popc(cbits);
+      obits |= (adj_t)bits << (c * P);
+      if (TWO_PASS) {
+        g_dx[c] = dx; g_dy[c] = dy; g_dvx[c] = evx - vx; g_dvy[c] = evy - vy; g_d[c] = dist;
+      } else {
+        const int pos = cnt_run + __popc(bits & low_mask(sub));
+        if (nb && pos < K && active) {
+          ((int32_t*)c_idx)[pos] = e_c[c];
+          T* f = (T*)c_feat + pos * GSM_NBR_FEAT_DIM;
+          st2<T>(f, dx, dy); st2<T>(f + 2, evx - vx, evy - vy); st2<T>(f + 4, dist, type_c[c]);
+        }
+        cnt_run += __popc(bits);
+      }
+    }
+    int cnt = sizeof(adj_t) == 4 ? __popc((uint32_t)obits) : __popcll((uint64_t)obits);
+    if (TWO_PASS) {
 #pragma unroll
-      for (int w = 0; w < W; w++) {
-        uint32_t cw = (nb && (e >> 5) == w) ? (1u << (e & 31)) : 0u;
-        // only words this chunk can touch are reduced (compile-time range)
-        if (w * 32 <= c * P + P && (w + 1) * 32 > c * P) {
-          if (P > 1) cw = __reduce_or_sync(grpmask, cw);
-          words[w] |= cw;
+      for (int c = 0; c < CH; c++) {
+        const int o = c * P + sub;
+        const adj_t below = obits & (((adj_t)1 << o) - 1);
+        const int rank = sizeof(adj_t) == 4 ? __popc((uint32_t)below) : __popcll((uint64_t)below);
+        const bool nb = (obits >> o) & 1;
+        const int pos = nb ? rank : cnt + (o - rank);
+        if (valid_c[c] && pos < K && active) {
+          ((int32_t*)c_idx)[pos] = nb ? e_c[c] : -1;
+          T* f = (T*)c_feat + pos * GSM_NBR_FEAT_DIM;
+          const T z = (T)0;
+          st2<T>(f, nb ? g_dx[c] : z, nb ? g_dy[c] : z);
+          st2<T>(f + 2, nb ? g_dvx[c] : z, nb ? g_dvy[c] : z);
+          st2<T>(f + 4, nb ? g_d[c] : z, nb ? type_c[c] : z);
+        }
+      }
+      if (cnt > K) cnt = K;
+    } else {
+      if (cnt > K) cnt = K;
+      if (active) {
+        for (int k = cnt + sub; k < K; k += P) {      // padding rows
+          ((int32_t*)c_idx)[k] = -1;
+          T* f = (T*)c_feat + k * GSM_NBR_FEAT_DIM;
+          st2<T>(f, (T)0, (T)0); st2<T>(f + 2, (T)0, (T)0); st2<T>(f + 4, (T)0, (T)0);
         }
       }
     }
-    if (cnt > K) cnt = K;
-    for (int k = cnt + sub; k < K; k += P) {          // padding rows
-      if (o_idx) g_idx[k] = -1;
-      if (o_feat) {
-        T* f = g_feat + k * GSM_NBR_FEAT_DIM;
-        st2<T>(f, (T)0, (T)0); st2<T>(f + 2, (T)0, (T)0); st2<T>(f + 4, (T)0, (T)0);
-      }
-    }
+    // entity-indexed adjacency: open a zero bit at my own index i
+    const adj_t lo_m = ((adj_t)1 << i) - 1;
+    const adj_t ebits = (obits & lo_m) | ((obits & ~lo_m) << 1);
 
-    // ---- SPEC §6-7: per-agent scalars ---------------------------------------------------------
+    // ---- SPEC §6-7: per-agent outputs, one role per lane ----------------------------------------
     const T gx = tx - px, gy = ty - py;
-    const T d = r_sqrt(gx * gx + gy * gy);
+    const T d = A::sqrt(gx * gx + gy * gy);
     T r = ((T)0 - p.w_dist * d) + (d < p.goal_tol ? p.w_goal : (T)0);
     if (p.share_reward) {
-      T s = shfl(envmask, r, env_base);
+      T s = shfl(FULL, r, env_base);
 #pragma unroll
-      for (int k = 1; k < N; k++) s = s + shfl(envmask, r, env_base + k * P);
+      for (int k = 1; k < N; k++) s = s + shfl(FULL, r, env_base + k * P);
       r = s / (T)N;
     }
-    if (sub == 0) {
-      if (o_obs) {
-        T* o = (T*)o_obs + row * GSM_OBS_DIM;
-        st2<T>(o, vx, vy); st2<T>(o + 2, px, py); st2<T>(o + 4, gx, gy);
-      }
-      if (o_cnt) ((int32_t*)o_cnt)[row] = cnt;
-      if (o_adj) {
+    if (active) {
+      if (P >= 3) {
+        if (sub < 3) st2<T>((T*)c_obs, sub == 0 ? vx : (sub == 1 ? px : gx), sub == 0 ? vy : (sub == 1 ? py : gy));
+      } else {
 #pragma unroll
-        for (int w = 0; w < W; w++) ((uint32_t*)o_adj)[row * W + w] = words[w];
+        for (int q = 0; q < OBS_PASSES; q++) {
+          const int part = sub + q * P;               // 0: (vx,vy) 1: (px,py) 2: (gx,gy)
+          if (part < 3) {
+            const T a0 = part == 0 ? vx : (part == 1 ? px : gx);
+            const T a1 = part == 0 ? vy : (part == 1 ? py : gy);
+            st2<T>((T*)(c_obs) + 2 * q * P, a0, a1);
+          }
+        }
       }
-      if (o_rew) ((T*)o_rew)[row] = r;
-      if (o_cost) ((T*)o_cost)[row] = (T)ncol;
-      if (o_done) o_done[row] = (uint8_t)(t_now >= p.episode_length);
-      if (o_asg) ((int32_t*)o_asg)[row] = asg;
+      const uint8_t dn = (uint8_t)(t_now >= p.episode_length);
+      if (ROLES) {
+        if (sizeof(T) == 4) {
+          const uint32_t v = ((uint32_t)cnt & rm0) | ((uint32_t)ebits & rm1) | (__float_as_uint((float)r) & rm2) |
+                             (__float_as_uint((float)ncol) & rm3) | ((uint32_t)asg & rm4);
+          if (sub < 5) *(uint32_t*)c_role = v;
+        } else {
+          const uint32_t v = ((uint32_t)cnt & rm0) | ((uint32_t)ebits & rm1) | ((uint32_t)asg & rm4);
+          if (sub == 0 || sub == 1 || sub == 4) *(uint32_t*)c_role = v;
+          if (sub == 2 || sub == 3) *(T*)c_role = sub == 2 ? r : (T)ncol;
+        }
+        if (sub == 5) *c_role = dn;
+      } else if (sub == 0) {
+        *(int32_t*)c_cnt = cnt;
+        *(uint32_t*)c_adj = (uint32_t)ebits;
+        if (W > 1) ((uint32_t*)c_adj)[1] = (uint32_t)((uint64_t)ebits >> 32);
+        *(T*)c_rew = r;
+        *(T*)c_cost = (T)ncol;
+        *(int32_t*)c_asg = asg;
+        *c_done = dn;
+      }
     }
-
-    // next slot of the rollout buffers
-    act_ptr += ss.actions;
-    if (o_obs) o_obs += ss.obs;
-    if (o_idx) o_idx += ss.nbr_idx;
-    if (o_feat) o_feat += ss.nbr_feat;
-    if (o_cnt) o_cnt += ss.nbr_cnt;
-    if (o_adj) o_adj += ss.adj;
-    if (o_rew) o_rew += ss.reward;
-    if (o_cost) o_cost += ss.cost;
-    if (o_done) o_done += ss.done;
-    if (o_asg) o_asg += ss.assign;
+    // advance the cursors to the next slot of the rollout buffers
+    c_idx += ss.nbr_idx; c_feat += ss.nbr_feat; c_obs += ss.obs;
+    if (ROLES) c_role += role_stride;
+    else {
+      c_cnt += ss.nbr_cnt; c_adj += ss.adj; c_rew += ss.reward; c_cost += ss.cost;
+      c_asg += ss.assign; c_done += ss.done;
+    }
   }
 
   // ---- state back to HBM ------------------------------------------------------------------------
-  if (sub == 0) {
+  if (sub == 0 && active) {
     T* a = p.agent_state + row * 4;
     st2<T>(a, px, py); st2<T>(a + 2, vx, vy);
     if (i == 0) p.t[env] = t_now;

@@ -72,7 +72,7 @@ static void fill_kparams(KParams<GSM_REAL>& kp, const HostParams& hp, const gsm_
   kp.own_goal_always = hp.own_goal_always;
   kp.envs_per_warp = envs_per_warp;
   kp.dt = (T)hp.dt; kp.one_minus_damp = (T)1 - (T)hp.damping;
-  kp.cf = (T)hp.cf; kp.km = (T)hp.km; kp.Rs = (T)hp.Rs;
+  kp.cf = (T)hp.cf; kp.km = (T)hp.km; kp.km_inv = (T)1 / (T)hp.km; kp.Rs = (T)hp.Rs;
   kp.w_dist = (T)hp.w_dist; kp.w_goal = (T)hp.w_goal; kp.goal_tol = (T)hp.goal_tol;
   kp.poly_r = (T)hp.poly_r;
   for (int a = 0; a < GSM_MAX_DISCRETE; a++) {
@@ -119,24 +119,37 @@ int GSM_SFX(launch_env)(const HostParams& hp, const LaunchPlan& plan, const gsm_
 // (scenario, N, L, P): P = lanes per agent, chosen so that N*P <= 32 and P covers as many of
 // the E-1 "other" entities per pass as a warp allows.
 #define GSM_SPEC_TABLE(X)                                                              \
-  X(GSM_SCN_NAVIGATION, 3, 6, 8) X(GSM_SCN_NAVIGATION, 6, 12, 4) X(GSM_SCN_NAVIGATION, 12, 24, 2) \
+  X(GSM_SCN_NAVIGATION, 3, 6, 4) X(GSM_SCN_NAVIGATION, 3, 6, 8) X(GSM_SCN_NAVIGATION, 3, 6, 2) \
+  X(GSM_SCN_NAVIGATION, 3, 6, 1)                                                       \
+  X(GSM_SCN_NAVIGATION, 6, 12, 4) X(GSM_SCN_NAVIGATION, 6, 12, 1)                      \
+  X(GSM_SCN_NAVIGATION, 12, 24, 2)                                                     \
   X(GSM_SCN_POLYGON, 3, 1, 4) X(GSM_SCN_POLYGON, 4, 1, 4) X(GSM_SCN_POLYGON, 5, 1, 4)  \
-  X(GSM_SCN_POLYGON, 6, 1, 4) X(GSM_SCN_POLYGON, 12, 1, 2)                             \
+  X(GSM_SCN_POLYGON, 6, 1, 4) X(GSM_SCN_POLYGON, 6, 1, 1) X(GSM_SCN_POLYGON, 12, 1, 2) \
   X(GSM_SCN_LINE, 3, 2, 4) X(GSM_SCN_LINE, 4, 2, 4) X(GSM_SCN_LINE, 5, 2, 4)           \
-  X(GSM_SCN_LINE, 6, 2, 4) X(GSM_SCN_LINE, 12, 2, 2)
+  X(GSM_SCN_LINE, 6, 2, 4) X(GSM_SCN_LINE, 6, 2, 1) X(GSM_SCN_LINE, 12, 2, 2)
 
 static bool spec_enabled() {
   return env_int("GSM_NO_SPEC", 0) == 0 && env_int("GSM_FORCE_P", 0) == 0 &&
          env_int("GSM_FORCE_CTA_ENV", -1) < 0;
 }
 
-static bool has_spec(const HostParams& hp) {
-  if (!spec_enabled()) return false;
-#define X(S, n, l, pp) if (hp.scenario == S && hp.N == n && hp.L == l) return true;
+// Lanes per agent of the specialised kernel for this handle (0: no instance).  The first
+// table entry of a (scenario, N, L) is the default; GSM_SPEC_P picks another compiled one.
+static int spec_P(const HostParams& hp) {
+  if (!spec_enabled()) return 0;
+  const int want = env_int("GSM_SPEC_P", 0);
+  int first = 0;
+#define X(S, n, l, pp)                                        \
+  if (hp.scenario == S && hp.N == n && hp.L == l) {           \
+    if (!first) first = pp;                                   \
+    if (want == pp) return pp;                                \
+  }
   GSM_SPEC_TABLE(X)
 #undef X
-  return false;
+  return first;
 }
+
+static bool has_spec(const HostParams& hp) { return spec_P(hp) != 0; }
 
 template <int SCN, int N, int L, int P>
 static int launch_spec_one(const KParams<GSM_REAL>& kp, int n_steps, const StepStrides& ss,
@@ -150,7 +163,8 @@ static int launch_spec_one(const KParams<GSM_REAL>& kp, int n_steps, const StepS
 
 int GSM_SFX(launch_spec)(const HostParams& hp, const gsm_step_io& io, int n_steps,
                          const RolloutStrides& rs, cudaStream_t st) {
-  if (!has_spec(hp)) return -1;
+  const int P = spec_P(hp);
+  if (!P) return -1;
   if (hp.n_envs == 0) return 0;
   KParams<GSM_REAL> kp;
   fill_kparams(kp, hp, io, 0, nullptr, 0);
@@ -159,7 +173,7 @@ int GSM_SFX(launch_spec)(const HostParams& hp, const gsm_step_io& io, int n_step
   ss.nbr_cnt = rs.nbr_cnt; ss.adj = rs.adj; ss.reward = rs.reward; ss.cost = rs.cost;
   ss.done = rs.done; ss.assign = rs.assign;
 #define X(S, n, l, pp) \
-  if (hp.scenario == S && hp.N == n && hp.L == l) return launch_spec_one<S, n, l, pp>(kp, n_steps, ss, st);
+  if (hp.scenario == S && hp.N == n && hp.L == l && P == pp) return launch_spec_one<S, n, l, pp>(kp, n_steps, ss, st);
   GSM_SPEC_TABLE(X)
 #undef X
   return -1;

@@ -47,8 +47,15 @@ def assert_match(got, want, *, rtol, atol, ctx="", int_exact=True, keys=None):
             np.testing.assert_allclose(g, w, rtol=rtol, atol=atol, err_msg=f"{ctx} {k}")
 
 
-def near_threshold_rows(cfg, bufs64, eps):
-    """Mask [n_envs, N] of agents whose fp64 neighbour/collision/goal predicates sit within
-    eps of a threshold (fp32 may legitimately flip those)."""
-    feat = bufs64["nbr_feat"]
-    return None if feat is None else None
+def near_threshold_rows(cfg, agent_state, landmark_pos, eps):
+    """Bool [n_envs, N]: agents with some pair distance within eps of the sensing radius or of
+    the contact distance (fp64 state).  fp32 may legitimately flip those predicates."""
+    N = cfg.n_agents
+    pos = np.concatenate([agent_state[..., :2], landmark_pos], axis=1).astype(np.float64)   # [B, E, 2]
+    d = np.sqrt(((pos[:, None, :, :] - pos[:, :N, None, :]) ** 2).sum(-1))                    # [B, N, E]
+    size = np.asarray(cfg.size, np.float64)
+    dmin = size[:N, None] + size[None, :]
+    near = (np.abs(d - cfg.sensing_radius) < eps) | (np.abs(d - dmin[None]) < eps)
+    for i in range(N):
+        near[:, i, i] = False
+    return near.any(-1)

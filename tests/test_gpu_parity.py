@@ -13,7 +13,8 @@ import pytest
 import torch
 
 from gs_marl_b200 import abi
-from tests._util import GOLDEN_TRAJ, golden_path, make_cfg, assert_match, random_actions, GOLDEN
+from tests._util import (GOLDEN_TRAJ, golden_path, make_cfg, assert_match, random_actions, GOLDEN,
+                         near_threshold_rows)
 
 pytestmark = pytest.mark.gpu
 
@@ -113,6 +114,33 @@ def test_f64_25_steps_vs_oracle(name, N, B, kw):
     env.close()
 
 
+@pytest.mark.parametrize("name,N,P", [("navigation", 3, 8), ("navigation", 3, 4), ("navigation", 3, 2),
+                                      ("navigation", 3, 1), ("navigation", 6, 4), ("navigation", 6, 1),
+                                      ("polygon", 6, 4), ("polygon", 6, 1), ("line", 6, 4), ("line", 6, 1)])
+@pytest.mark.parametrize("kw", [{}, {"max_nbrs": 3, "share_reward": True}])
+def test_specialised_kernel_variants_f64(name, N, P, kw, monkeypatch):
+    """Every compiled (scenario, N, L, P) instance of the register-resident kernel, single
+    steps and one fused 25-step launch, against the oracle."""
+    monkeypatch.setenv("GSM_SPEC_P", str(P))
+    cfg = make_cfg(name, N, "f64", **kw)
+    B, T = 77, 25
+    o = _squeezed_start(cfg, B, 31 + N)
+    env = _env(cfg, B)
+    env.set_state(o.agent_state, o.landmark_pos, o.step_count)
+    rng = np.random.default_rng(P)
+    acts = random_actions(cfg, rng, (T, B))
+    wants = [{k: v.copy() for k, v in o.step(acts[t]).items()} for t in range(T)]
+    roll = _np(env.rollout(acts))
+    for t in range(T):
+        assert_match({k: roll[k][t] for k in OUT_KEYS}, wants[t], rtol=F64_RTOL, atol=F64_ATOL,
+                     ctx=f"{name}{N} P={P} fused t={t}")
+    env.set_state(o.agent_state * 0 + _squeezed_start(cfg, B, 31 + N).agent_state, o.landmark_pos, np.zeros(B, np.int32))
+    for t in range(3):
+        env.step(acts[t])
+        assert_match(_np(env.buf), wants[t], rtol=F64_RTOL, atol=F64_ATOL, ctx=f"{name}{N} P={P} step t={t}")
+    env.close()
+
+
 @pytest.mark.parametrize("name,N,B,kw", [c for c in CASES if c[1] <= 12])
 def test_f32_one_step_within_1e4(name, N, B, kw):
     """Production precision: one step from identical (fp32-representable) states."""
@@ -130,11 +158,16 @@ def test_f32_one_step_within_1e4(name, N, B, kw):
     ag = env.get_state()[0].cpu().numpy()
     np.testing.assert_allclose(ag, o.agent_state, rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(got["obs"], want["obs"], rtol=1e-4, atol=1e-5)
-    # integer outputs: identical except where an fp64 predicate sits within 1e-5 of its threshold
-    same = (got["nbr_cnt"] == want["nbr_cnt"]) & (got["cost"] == want["cost"]) & \
-           (got["adj"] == want["adj"]).all(-1)
-    assert same.mean() > 0.995, same.mean()
-    ok = same & (got["assign"] == want["assign"])
+    # integer outputs: bit-identical wherever no fp64 predicate sits within 1e-5 of its threshold
+    # (the UNVERIFIED preset has contact_force*dt^2/mass == 1, so resting contacts land exactly
+    # on dist == dmin and fp32 may round the collision flag either way)
+    near = near_threshold_rows(cfg64, o.agent_state, o.landmark_pos, 1e-5)
+    assert near.mean() < 0.05
+    ok = ~near
+    for k in ("nbr_cnt", "cost", "nbr_idx", "adj"):
+        g, w = got[k][ok], want[k][ok]
+        assert (g == w).all(), (k, int((g != w).sum()))
+    ok = ok & (got["assign"] == want["assign"])
     np.testing.assert_allclose(got["reward"][ok], want["reward"][ok], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(got["nbr_feat"][ok], want["nbr_feat"][ok], rtol=1e-4, atol=1e-5)
     env.close()
