@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -74,9 +74,11 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Median SM clock of the samples that arrived inside [t0, t1] (the timed region); if the
+        region was shorter than the sampling period, of all samples taken under load."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -84,22 +86,30 @@ class ClockSampler:
             self.proc.wait(2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+
+        def parse(rows):
+            sm, mx, reasons = [], [], set()
+            for _, ln in rows:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, mx, reasons
+        inside = [r for r in self.lines if t0 is not None and t0 <= r[0] <= t1]
+        window = "timed region"
+        if not inside:
+            inside, window = self.lines, "warm-up + timed region (region shorter than the 50 ms sampling period)"
+        sm, mx, reasons = parse(inside)
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def measured_peak():
@@ -266,6 +276,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     K, W, T = args.steps, args.warmup, ROLLOUT_T
+    spec_p = os.environ.get("GSM_SPEC_P", "4 (default)")
     cfg = scenarios.load("navigation").make_world(N_AGENTS, dtype="f32", episode_length=T)
     env = MultiAgentGraphConstrainEnv(cfg, args.envs, device=local, env_offset=rank * args.envs, seed=1)
     env.reset()
@@ -287,20 +298,22 @@ def run_gpu(args):
                 io = env._make_io(io_bufs, acts[s])
                 env._check(env.lib.gsm_step(env._h, __import__("ctypes").byref(io), env._stream()))
 
+    sampler = ClockSampler(local); sampler.start()
     run_steps(max(W, 3))
     barrier()
-    sampler = ClockSampler(local); sampler.start()
     l0 = env.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     ev0.record()
     run_steps(K)
     ev1.record()
     barrier()
+    wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
     launches = env.kernel_launches - l0
     n_resets = (K + T - 1) // T
-    clocks = sampler.stop()
+    clocks = sampler.stop(wall0, wall1)
 
     # dominant kernel alone: K env-kernel launches, no resets, CUDA events on the same stream
     env.reset()
@@ -314,6 +327,32 @@ def run_gpu(args):
     k1.record()
     torch.cuda.synchronize()
     kern_ms = k0.elapsed_time(k1) / (reps * T)
+
+    # ---- same kernel at a batch that saturates the GPU (explains the small-batch fraction) -------
+    large = None
+    if world == 1 and args.large_envs > 0:
+        nl = args.large_envs
+        big = MultiAgentGraphConstrainEnv(cfg, nl, device=local, seed=2)
+        big.reset()
+        Tl = 8
+        bacts = torch.randint(0, 5, (Tl, nl, N_AGENTS), generator=gen, device=dev, dtype=torch.int32)
+        bring = {k: big._alloc(k, (Tl,)) for k in big.OUTPUTS}
+        big.rollout(bacts, out=bring)
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(5):
+            big.rollout(bacts, out=bring)
+        b1.record()
+        torch.cuda.synchronize()
+        step_ms = b0.elapsed_time(b1) / (5 * Tl)
+        gbs = cfg.bytes_per_agent_step() * nl * N_AGENTS / (step_ms * 1e-3) / 1e9
+        pk, _ = measured_peak()
+        large = {"envs": nl, "step_us": step_ms * 1e3, "achieved": gbs, "unit": "GB/s", "frac": gbs / pk,
+                 "agent_steps_per_s": nl * N_AGENTS / (step_ms * 1e-3),
+                 "buffer_mb": sum(v.numel() * v.element_size() for v in bring.values()) / 1e6}
+        big.close()
+        del bring, bacts
 
     # ---- e2e through the numpy-facing drop-in ------------------------------------------------
     vec = GraphVecEnv(cfg, args.envs, device=local, env_offset=rank * args.envs, seed=1)
@@ -347,6 +386,10 @@ def run_gpu(args):
         peak, peak_src = measured_peak()
         bytes_launch = cfg.bytes_per_agent_step() * args.envs * N_AGENTS
         achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
+        # exact bytes of one fused T-step launch: state read+written once, not every step
+        state_rw = 2 * 4 * 4 * args.envs * N_AGENTS
+        bytes_fused = T * (bytes_launch - state_rw) + state_rw
+        achieved_fused = bytes_fused / (kern_ms * T * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -365,8 +408,12 @@ def run_gpu(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(),
-                         "kernel": "gsm::env_kernel<float,1,false,true>",
-                         "launch_us": kern_ms * 1e3, "algorithmic_bytes_per_launch": bytes_launch,
+                         "kernel": f"gsm::env_steps_kernel<float, NAVIGATION, 3, 6, P={spec_p}> "
+                                   f"(one launch = {T} fused steps; achieved is per step)",
+                         "launch_us": kern_ms * 1e3 * T, "step_us": kern_ms * 1e3,
+                         "algorithmic_bytes_per_launch": bytes_launch * T,
+                         "algorithmic_bytes_per_step": bytes_launch,
+                         "frac_fused_exact": achieved_fused / peak,
                          "bytes_per_agent_step": cfg.bytes_per_agent_step(), "peak_source": peak_src,
                          "note": "layout is the declared one of SPEC.md §6 (reference layout unknown)"},
             "final_stats": totals,
@@ -385,6 +432,9 @@ def run_gpu(args):
                 "sample": f"reference-STYLE numpy port (oracle/py_env.py; GS-MARL's own env is withheld), "
                           f"fp64, {envs} envs x 10 steps in {cores} subprocess workers"}
             line["cpu_baseline_c_port"] = cpu_c_oracle_rate()
+        if world == 1 and args.large_envs > 0:
+            line["roofline_large_batch"] = large
+
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:
@@ -394,8 +444,10 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=100000)
+    ap.add_argument("--warmup", type=int, default=1000)
+    ap.add_argument("--large-envs", type=int, default=1048576,
+                    help="extra roofline line at a GPU-saturating env count (0 = skip)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=200)
