@@ -196,11 +196,12 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         if (a >= 0 && a < p.n_actions) { ux = p.discrete_u[a][0]; uy = p.discrete_u[a][1]; }
       }
       if (sub == 0) { fx = accel_i * ux; fy = accel_i * uy; }
-      c_act += ss.actions;
-      if (step + 1 < n_steps) {
-        if (p.action_mode == GSM_ACT_DISCRETE) act_next = *(const int32_t*)c_act;
-        else { actx_next = ((const T*)c_act)[0]; acty_next = ((const T*)c_act)[1]; }
-      }
+      // Unconditional load (the last step re-reads its own, valid, address): a load under
+      // `if (step + 1 < n_steps)` becomes LDG + predicated MOV in the same iteration and the
+      // warp then waits out the whole memory latency here instead of one step later.
+      if (step + 1 < n_steps) c_act += ss.actions;
+      if (p.action_mode == GSM_ACT_DISCRETE) act_next = *(const int32_t*)c_act;
+      else { actx_next = ((const T*)c_act)[0]; acty_next = ((const T*)c_act)[1]; }
     }
     // ---- SPEC §3: pair forces ---------------------------------------------------------------
 #pragma unroll
