@@ -175,7 +175,8 @@ int do_env(gsm_env* h, const gsm_step_io& io, int physics, const uint8_t* mask, 
 }
 
 // One env step (physics + outputs): the size-specialised kernel when the handle has one.
-int do_steps(gsm_env* h, const gsm_step_io& io, int n_steps, cudaStream_t st) {
+int do_steps(gsm_env* h, const gsm_step_io& io, int n_steps, cudaStream_t st, int observe = 0,
+             const uint8_t* mask = nullptr, int64_t mask_stride = 0) {
   for (int k = IO_OBS; k < IO_COUNT; k++)
     if (!io_get(io, k)) return -1000;   // the specialised kernel writes every output
   gsm::RolloutStrides rs;
@@ -187,19 +188,33 @@ int do_steps(gsm_env* h, const gsm_step_io& io, int n_steps, cudaStream_t st) {
     rs.reward = (int64_t)h->io_bytes[IO_REWARD]; rs.cost = (int64_t)h->io_bytes[IO_COST];
     rs.done = (int64_t)h->io_bytes[IO_DONE]; rs.assign = (int64_t)h->io_bytes[IO_ASSIGN];
   }
-  const int e = is_f32(h) ? gsm::launch_spec_f32(h->hp, io, n_steps, rs, st)
-                          : gsm::launch_spec_f64(h->hp, io, n_steps, rs, st);
-  if (e > 0) return cuda_fail(h, e, "specialised env kernel launch");
+  int e = -1;
+  if (h->plan.spec)
+    e = is_f32(h) ? gsm::launch_spec_f32(h->hp, io, n_steps, rs, observe, mask, mask_stride, st)
+                  : gsm::launch_spec_f64(h->hp, io, n_steps, rs, observe, mask, mask_stride, st);
+  else if (h->plan.big && !observe)
+    e = is_f32(h) ? gsm::launch_big_f32(h->hp, io, n_steps, rs, st)
+                  : gsm::launch_big_f64(h->hp, io, n_steps, rs, st);
+  if (e > 0) return cuda_fail(h, e, "fused env kernel launch");
   if (e == 0) { h->launches += 1; return 0; }
-  return -1000;      // no instance
+  return -1000;      // no fused kernel for this handle / call
 }
 
 int do_step(gsm_env* h, const gsm_step_io& io, cudaStream_t st) {
-  if (h->plan.spec) {
+  if (h->plan.spec || h->plan.big) {
     const int r = do_steps(h, io, 1, st);
     if (r != -1000) return r;
   }
   return do_env(h, io, 1, nullptr, 0, st);
+}
+
+// Observation + graph of the current state (no physics), optionally for masked envs only.
+int do_observe(gsm_env* h, const gsm_step_io& io, const uint8_t* mask, int64_t stride, cudaStream_t st) {
+  if (h->plan.spec) {
+    const int r = do_steps(h, io, 1, st, 1, mask, stride);
+    if (r != -1000) return r;
+  }
+  return do_env(h, io, 0, mask, stride, st);
 }
 
 bool any_obs_output(const gsm_step_io& io) {
@@ -389,7 +404,7 @@ int gsm_reset(gsm_env* h, uint64_t seed, const uint8_t* mask, int64_t mask_strid
                           : gsm::launch_reset_f64(h->hp, seed, mask, mask_stride, st);
   if (e) return cuda_fail(h, e, "reset kernel launch");
   h->launches += 2;
-  if (io && any_obs_output(*io)) return do_env(h, *io, 0, mask, mask ? mask_stride : 0, st);
+  if (io && any_obs_output(*io)) return do_observe(h, *io, mask, mask ? mask_stride : 0, st);
   return GSM_OK;
 }
 
@@ -403,14 +418,14 @@ int gsm_step(gsm_env* h, const gsm_step_io* io, void* stream) {
 int gsm_observe(gsm_env* h, const gsm_step_io* io, void* stream) {
   if (!h || !io) return GSM_ERR_INVALID_ARG;
   DeviceGuard guard(h->device);
-  return do_env(h, *io, 0, nullptr, 0, (cudaStream_t)stream);
+  return do_observe(h, *io, nullptr, 0, (cudaStream_t)stream);
 }
 
 int gsm_rollout(gsm_env* h, int32_t n_steps, const gsm_step_io* io, void* stream) {
   if (!h || !io || n_steps < 1) return GSM_ERR_INVALID_ARG;
   if (!io->actions) return fail(h, GSM_ERR_INVALID_ARG, "io.actions is NULL");
   DeviceGuard guard(h->device);
-  if (h->plan.spec) {               // fused: all n_steps in one launch, state stays in registers
+  if (h->plan.spec || h->plan.big) {   // fused: all n_steps in one launch, state stays on chip
     const int r = do_steps(h, *io, n_steps, (cudaStream_t)stream);
     if (r != -1000) return r;
   }
@@ -517,7 +532,7 @@ int gsm_observe_host(gsm_env* h, const gsm_step_io* io) {
   DeviceGuard guard(h->device);
   int st = ensure_host_path(h);
   if (st) return st;
-  st = do_env(h, h->d_io, 0, nullptr, 0, h->stream);
+  st = do_observe(h, h->d_io, nullptr, 0, h->stream);
   if (st) return st;
   return copy_out(h, *io, false);
 }

@@ -34,6 +34,7 @@ struct LaunchPlan {     // chosen once per handle
   size_t smem;
   int64_t grid;
   int spec;             // 1: a size-specialised register-resident kernel exists (gsm_kernels_spec.cuh)
+  int big;              // 1: the large-team CTA-per-env kernel applies (gsm_kernels_big.cuh)
 };
 
 // Each returns a cudaError_t (as int).  physics: 1 = full step, 0 = observe only.
@@ -45,10 +46,18 @@ int launch_env_f64(const HostParams& hp, const LaunchPlan& plan, const gsm_step_
                    const uint8_t* mask, int64_t mask_stride, cudaStream_t st);
 // n_steps consecutive steps in ONE launch of the specialised kernel; returns -1 if the
 // handle's (scenario, N, L) has no compiled instance.
+// observe != 0: observe-only variant (reset path) with an optional per-env mask.
 int launch_spec_f32(const HostParams& hp, const gsm_step_io& io, int n_steps,
-                    const RolloutStrides& rs, cudaStream_t st);
+                    const RolloutStrides& rs, int observe, const uint8_t* mask,
+                    int64_t mask_stride, cudaStream_t st);
 int launch_spec_f64(const HostParams& hp, const gsm_step_io& io, int n_steps,
-                    const RolloutStrides& rs, cudaStream_t st);
+                    const RolloutStrides& rs, int observe, const uint8_t* mask,
+                    int64_t mask_stride, cudaStream_t st);
+// Large-team navigation kernel (n_steps fused); returns -1 if it does not apply.
+int launch_big_f32(const HostParams& hp, const gsm_step_io& io, int n_steps,
+                   const RolloutStrides& rs, cudaStream_t st);
+int launch_big_f64(const HostParams& hp, const gsm_step_io& io, int n_steps,
+                   const RolloutStrides& rs, cudaStream_t st);
 int launch_reset_f32(const HostParams& hp, uint64_t seed, const uint8_t* mask, int64_t mask_stride,
                      cudaStream_t st);
 int launch_reset_f64(const HostParams& hp, uint64_t seed, const uint8_t* mask, int64_t mask_stride,

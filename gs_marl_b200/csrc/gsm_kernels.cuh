@@ -160,7 +160,7 @@ __device__ int lsa_lanes(const T* __restrict__ C, int n, int col, unsigned gm, i
     int i = cur, nrem = n, sink = -1;
     int pos = n - 1 - col;
     bool inrem = is_col, sr_m = false, sc_m = false;
-    while (sink == -1) {
+    for (int iter = 0; iter < n && sink == -1; iter++) {
       if (col == i) sr_m = true;
       const T u_i = shfl(gm, u_m, base + i);
       if (inrem) {
@@ -190,14 +190,91 @@ __device__ int lsa_lanes(const T* __restrict__ C, int n, int col, unsigned gm, i
       else if (sr_m) u_m += minval - spc_row;
     }
     if (sc_m) v_m -= minval - spc;
+    if (sink < 0) return -1;                        // non-finite costs: give up, never hang
     int j = sink;
-    for (;;) {
+    for (int iter = 0; iter < n; iter++) {
       const int a = shfl(gm, path_m, base + j);
       if (col == j) row4col_m = a;
       const int tprev = shfl(gm, col4row_m, base + a);
       if (col == a) col4row_m = j;
       j = tprev;
       if (a == cur) break;
+    }
+  }
+  return col4row_m;
+}
+
+// Segmented, lockstep form of lsa_lanes for several problems per warp.  Every lane of the
+// warp calls it (full-mask primitives only).  A segment is a run of consecutive lanes
+// starting at `base` that holds one problem; lane offset `off` < N of a segment is column
+// `off`, row `off` AND slot `off` of scipy's `remaining` array (rem = column stored at that
+// position), so the scan "last unassigned minimum in position order, else first minimum"
+// is clz / ffs on two ballots.  Segments whose search has ended idle until the slowest one
+// finishes (time = max, not sum, of the per-problem iteration counts).  All loops are bounded
+// by N so that non-finite costs cannot hang the warp.  Returns col4row for row == off.
+template <typename T, int N>
+__device__ __forceinline__ int lsa_seg(const T* __restrict__ C, int off, int base, bool live) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const T INF = r_inf<T>();
+  const bool is_col = live && off < N;
+  T u_m = 0, v_m = 0;
+  int col4row_m = -1, row4col_m = -1, path_m = -1;
+  for (int cur = 0; cur < N; cur++) {
+    T minval = 0, spc = INF;
+    int i = cur, nrem = N, sink = live ? -1 : 0;
+    int rem = N - 1 - off;                          // remaining[] filled in reverse
+    bool inrem = is_col, sr_m = false, sc_m = false;
+    for (int iter = 0; iter < N && __any_sync(FULL, sink == -1); iter++) {
+      const bool run = sink == -1;
+      if (run && off == i) sr_m = true;
+      const T u_i = shfl(FULL, u_m, base + i);
+      if (run && inrem) {
+        const T r = minval + C[i * N + off] - u_i - v_m;
+        if (r < spc) { path_m = i; spc = r; }
+      }
+      const T mine = inrem ? spc : INF;
+      T lowest = INF;
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        const T o = shfl(FULL, mine, base + k);
+        lowest = o < lowest ? o : lowest;
+      }
+      const int rc = off < N ? rem : 0;
+      const T spc_of = shfl(FULL, spc, base + rc);
+      const int r4c_of = shfl(FULL, row4col_m, base + rc);
+      const bool cand = is_col && off < nrem && spc_of == lowest;
+      const bool ucand = cand && r4c_of == -1;
+      const unsigned bc = (__ballot_sync(FULL, cand) >> base) & low_mask(N);
+      const unsigned bu = (__ballot_sync(FULL, ucand) >> base) & low_mask(N);
+      const int it_sel = bu ? (31 - __clz(bu)) : (bc ? __ffs(bc) - 1 : 0);
+      const int j = shfl(FULL, rem, base + it_sel);
+      const int r4c_j = shfl(FULL, row4col_m, base + j);
+      const int last = shfl(FULL, rem, base + nrem - 1);
+      if (run) {
+        minval = lowest;
+        if (r4c_j == -1) sink = j; else i = r4c_j;
+        if (off == j) { sc_m = true; inrem = false; }
+        if (off == it_sel) rem = last;
+        nrem--;
+      }
+    }
+    const T spc_row = shfl(FULL, spc, base + (col4row_m >= 0 ? col4row_m : 0));
+    if (is_col) {
+      if (off == cur) u_m += minval;
+      else if (sr_m) u_m += minval - spc_row;
+    }
+    if (sc_m) v_m -= minval - spc;
+    int j = sink;
+    bool going = live && sink >= 0;
+    for (int iter = 0; iter < N && __any_sync(FULL, going); iter++) {
+      const int a = shfl(FULL, path_m, base + j);
+      const int tprev = shfl(FULL, col4row_m, base + a);
+      if (going) {
+        if (off == j) row4col_m = a;
+        if (off == a) col4row_m = j;
+        j = tprev;
+        if (a == cur) going = false;
+      }
     }
   }
   return col4row_m;

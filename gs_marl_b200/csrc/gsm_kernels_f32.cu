@@ -1,5 +1,5 @@
 // Production precision (fp32).  FMA contraction allowed.
-#include "gsm_kernels_spec.cuh"
+#include "gsm_kernels_big.cuh"
 #define GSM_REAL float
 #define GSM_SFX(name) name##_f32
 #include "gsm_launch.inl"

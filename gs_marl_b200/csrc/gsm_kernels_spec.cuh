@@ -58,7 +58,9 @@ template <> struct AdjBits<0> { typedef uint32_t type; };
 // Every output pointer must be non-NULL (the API layer falls back to the generic kernel
 // otherwise).  All 32 lanes stay alive and use FULL-mask warp primitives: lanes without a
 // real env compute on a clamped env index and only their stores are predicated off.
-template <typename T, int SCN, int N, int L, int P>
+// OBS = true: observe only (reset path) — no physics, no reward/cost/done, one "step",
+// optional per-env mask (p.mask); the state is not written back.
+template <typename T, int SCN, int N, int L, int P, bool OBS>
 __global__ void __launch_bounds__(kSpecThreads)
 env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
                  const __grid_constant__ StepStrides ss) {
@@ -78,7 +80,8 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   const int off = lane - eiw * LPE;
   const int i = off / P, sub = off % P;             // my agent, my lane in its group
   const int64_t env_raw = ((int64_t)blockIdx.x * (kSpecThreads / 32) + warp) * EPW + eiw;
-  const bool active = eiw < EPW && env_raw < p.n_envs;
+  bool active = eiw < EPW && env_raw < p.n_envs;
+  if (OBS && p.mask != nullptr && active) active = p.mask[env_raw * p.mask_stride] != 0;
   const int64_t env = active ? env_raw : 0;         // idle lanes shadow env 0, never store
   const int env_base = eiw * LPE;
   const int grp_base = env_base + i * P;
@@ -182,13 +185,15 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
 
   int act_next = 0;
   T actx_next = 0, acty_next = 0;
-  if (p.action_mode == GSM_ACT_DISCRETE) act_next = *(const int32_t*)c_act;
-  else { actx_next = ((const T*)c_act)[0]; acty_next = ((const T*)c_act)[1]; }
+  if (!OBS) {
+    if (p.action_mode == GSM_ACT_DISCRETE) act_next = *(const int32_t*)c_act;
+    else { actx_next = ((const T*)c_act)[0]; acty_next = ((const T*)c_act)[1]; }
+  }
 
   for (int step = 0; step < n_steps; step++) {
     // ---- SPEC §2: action force; the next step's action is prefetched -------------------------
     T fx = 0, fy = 0;
-    {
+    if (!OBS) {
       T ux = actx_next, uy = acty_next;
       if (p.action_mode == GSM_ACT_DISCRETE) {
         const int a = act_next;
@@ -205,7 +210,7 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     }
     // ---- SPEC §3: pair forces ---------------------------------------------------------------
 #pragma unroll
-    for (int c = 0; c < CH; c++) {
+    for (int c = 0; c < (OBS ? 0 : CH); c++) {
       T qx = lmx[c], qy = lmy[c];
       if (c * P < N - 1) {                           // this chunk can hold agent pairs
         const T ax = shfl(FULL, px, src_c[c]), ay = shfl(FULL, py, src_c[c]);
@@ -222,7 +227,7 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         }
       }
     }
-    if (P > 1) {
+    if (P > 1 && !OBS) {
 #pragma unroll
       for (int m = P / 2; m >= 1; m >>= 1) {
         fx += __shfl_xor_sync(FULL, fx, m);
@@ -230,6 +235,7 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       }
     }
     // ---- SPEC §4: integration, redundantly on the P lanes of the agent --------------------
+    if (!OBS) {
     vx = vx * p.one_minus_damp; vy = vy * p.one_minus_damp;
     vx = vx + A::div_const(fx, mass_i, mass_inv) * p.dt;
     vy = vy + A::div_const(fy, mass_i, mass_inv) * p.dt;
@@ -239,6 +245,7 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     }
     px = px + vx * p.dt; py = py + vy * p.dt;
     t_now += 1;
+    }
 
     // ---- SPEC §5: assignment (polygon / line) -----------------------------------------------
     T tx = goalx, ty = goaly;
@@ -254,8 +261,8 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         }
       }
       __syncwarp();
-      int a_row = 0;
-      if (eiw < EPW) a_row = lsa_lanes<T>(s_cm, N, off, envmask, env_base);   // col4row, row == off
+      // all envs of the warp are solved in lockstep; lanes off < N are the columns / rows
+      const int a_row = lsa_seg<T, N>(s_cm, off, env_base, eiw < EPW);
       __syncwarp();
       asg = shfl(FULL, a_row, env_base + i);
       tx = shfl(FULL, slotx, env_base + asg);
@@ -368,21 +375,19 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         if (sizeof(T) == 4) {
           const uint32_t v = ((uint32_t)cnt & rm0) | ((uint32_t)ebits & rm1) | (__float_as_uint((float)r) & rm2) |
                              (__float_as_uint((float)ncol) & rm3) | ((uint32_t)asg & rm4);
-          if (sub < 5) *(uint32_t*)c_role = v;
+          if (OBS ? (sub == 0 || sub == 1 || sub == 4) : (sub < 5)) *(uint32_t*)c_role = v;
         } else {
           const uint32_t v = ((uint32_t)cnt & rm0) | ((uint32_t)ebits & rm1) | ((uint32_t)asg & rm4);
           if (sub == 0 || sub == 1 || sub == 4) *(uint32_t*)c_role = v;
-          if (sub == 2 || sub == 3) *(T*)c_role = sub == 2 ? r : (T)ncol;
+          if (!OBS && (sub == 2 || sub == 3)) *(T*)c_role = sub == 2 ? r : (T)ncol;
         }
-        if (sub == 5) *c_role = dn;
+        if (!OBS && sub == 5) *c_role = dn;
       } else if (sub == 0) {
         *(int32_t*)c_cnt = cnt;
         *(uint32_t*)c_adj = (uint32_t)ebits;
         if (W > 1) ((uint32_t*)c_adj)[1] = (uint32_t)((uint64_t)ebits >> 32);
-        *(T*)c_rew = r;
-        *(T*)c_cost = (T)ncol;
+        if (!OBS) { *(T*)c_rew = r; *(T*)c_cost = (T)ncol; *c_done = dn; }
         *(int32_t*)c_asg = asg;
-        *c_done = dn;
       }
     }
     // advance the cursors to the next slot of the rollout buffers
@@ -395,7 +400,7 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   }
 
   // ---- state back to HBM ------------------------------------------------------------------------
-  if (sub == 0 && active) {
+  if (!OBS && sub == 0 && active) {
     T* a = p.agent_state + row * 4;
     st2<T>(a, px, py); st2<T>(a + 2, vx, vy);
     if (i == 0) p.t[env] = t_now;

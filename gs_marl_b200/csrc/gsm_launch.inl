@@ -11,6 +11,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 static bool has_spec(const HostParams& hp);
+static bool has_big(const HostParams& hp);
 static int next_pow2(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
 int GSM_SFX(plan)(const HostParams& hp, LaunchPlan* plan) {
@@ -41,6 +42,7 @@ int GSM_SFX(plan)(const HostParams& hp, LaunchPlan* plan) {
   plan->grid = (hp.n_envs + plan->envs_per_cta - 1) / plan->envs_per_cta;
   if (plan->smem > 227 * 1024) return (int)cudaErrorInvalidValue;
   plan->spec = has_spec(hp) ? 1 : 0;
+  plan->big = (!plan->spec && has_big(hp)) ? 1 : 0;
   return 0;
 }
 
@@ -123,10 +125,12 @@ int GSM_SFX(launch_env)(const HostParams& hp, const LaunchPlan& plan, const gsm_
   X(GSM_SCN_NAVIGATION, 3, 6, 1)                                                       \
   X(GSM_SCN_NAVIGATION, 6, 12, 4) X(GSM_SCN_NAVIGATION, 6, 12, 1)                      \
   X(GSM_SCN_NAVIGATION, 12, 24, 2)                                                     \
-  X(GSM_SCN_POLYGON, 3, 1, 4) X(GSM_SCN_POLYGON, 4, 1, 4) X(GSM_SCN_POLYGON, 5, 1, 4)  \
-  X(GSM_SCN_POLYGON, 6, 1, 4) X(GSM_SCN_POLYGON, 6, 1, 1) X(GSM_SCN_POLYGON, 12, 1, 2) \
-  X(GSM_SCN_LINE, 3, 2, 4) X(GSM_SCN_LINE, 4, 2, 4) X(GSM_SCN_LINE, 5, 2, 4)           \
-  X(GSM_SCN_LINE, 6, 2, 4) X(GSM_SCN_LINE, 6, 2, 1) X(GSM_SCN_LINE, 12, 2, 2)
+  X(GSM_SCN_POLYGON, 3, 1, 1) X(GSM_SCN_POLYGON, 4, 1, 1) X(GSM_SCN_POLYGON, 5, 1, 1)  \
+  X(GSM_SCN_POLYGON, 6, 1, 1) X(GSM_SCN_POLYGON, 6, 1, 4) X(GSM_SCN_POLYGON, 12, 1, 1) \
+  X(GSM_SCN_POLYGON, 12, 1, 2)                                                         \
+  X(GSM_SCN_LINE, 3, 2, 1) X(GSM_SCN_LINE, 4, 2, 1) X(GSM_SCN_LINE, 5, 2, 1)           \
+  X(GSM_SCN_LINE, 6, 2, 1) X(GSM_SCN_LINE, 6, 2, 4) X(GSM_SCN_LINE, 12, 2, 1)          \
+  X(GSM_SCN_LINE, 12, 2, 2)
 
 static bool spec_enabled() {
   return env_int("GSM_NO_SPEC", 0) == 0 && env_int("GSM_FORCE_P", 0) == 0 &&
@@ -153,18 +157,50 @@ static bool has_spec(const HostParams& hp) { return spec_P(hp) != 0; }
 
 template <int SCN, int N, int L, int P>
 static int launch_spec_one(const KParams<GSM_REAL>& kp, int n_steps, const StepStrides& ss,
-                           cudaStream_t st) {
+                           bool observe, cudaStream_t st) {
   constexpr int EPW = 32 / (N * P), WPC = kSpecThreads / 32;
   const int64_t grid = (kp.n_envs + EPW * WPC - 1) / (EPW * WPC);
   const size_t smem = SCN == GSM_SCN_NAVIGATION ? 0 : (size_t)WPC * EPW * N * N * sizeof(GSM_REAL);
-  env_steps_kernel<GSM_REAL, SCN, N, L, P><<<(unsigned)grid, kSpecThreads, smem, st>>>(kp, n_steps, ss);
+  if (observe)
+    env_steps_kernel<GSM_REAL, SCN, N, L, P, true><<<(unsigned)grid, kSpecThreads, smem, st>>>(kp, 1, ss);
+  else
+    env_steps_kernel<GSM_REAL, SCN, N, L, P, false><<<(unsigned)grid, kSpecThreads, smem, st>>>(kp, n_steps, ss);
   return (int)cudaGetLastError();
 }
 
 int GSM_SFX(launch_spec)(const HostParams& hp, const gsm_step_io& io, int n_steps,
-                         const RolloutStrides& rs, cudaStream_t st) {
+                         const RolloutStrides& rs, int observe, const uint8_t* mask,
+                         int64_t mask_stride, cudaStream_t st) {
   const int P = spec_P(hp);
   if (!P) return -1;
+  if (hp.n_envs == 0) return 0;
+  KParams<GSM_REAL> kp;
+  fill_kparams(kp, hp, io, 0, mask, mask_stride);
+  StepStrides ss;
+  ss.actions = rs.actions; ss.obs = rs.obs; ss.nbr_idx = rs.nbr_idx; ss.nbr_feat = rs.nbr_feat;
+  ss.nbr_cnt = rs.nbr_cnt; ss.adj = rs.adj; ss.reward = rs.reward; ss.cost = rs.cost;
+  ss.done = rs.done; ss.assign = rs.assign;
+#define X(S, n, l, pp) \
+  if (hp.scenario == S && hp.N == n && hp.L == l && P == pp) return launch_spec_one<S, n, l, pp>(kp, n_steps, ss, observe != 0, st);
+  GSM_SPEC_TABLE(X)
+#undef X
+  return -1;
+}
+
+// ---- large-team kernel (gsm_kernels_big.cuh) -------------------------------------------------
+static size_t big_smem(const HostParams& hp) {
+  return make_big_layout((int)sizeof(GSM_REAL), (int)sizeof(Ent<GSM_REAL>), hp.N, hp.N + hp.L, hp.K,
+                         kBigThreads / 32).total;
+}
+static bool has_big(const HostParams& hp) {
+  if (env_int("GSM_NO_BIG", 0) != 0 || env_int("GSM_FORCE_P", 0) != 0 || env_int("GSM_FORCE_CTA_ENV", -1) >= 0)
+    return false;
+  return hp.scenario == GSM_SCN_NAVIGATION && hp.N > 12 && hp.K % 4 == 0 && big_smem(hp) <= 200 * 1024;
+}
+
+int GSM_SFX(launch_big)(const HostParams& hp, const gsm_step_io& io, int n_steps,
+                        const RolloutStrides& rs, cudaStream_t st) {
+  if (!has_big(hp)) return -1;
   if (hp.n_envs == 0) return 0;
   KParams<GSM_REAL> kp;
   fill_kparams(kp, hp, io, 0, nullptr, 0);
@@ -172,11 +208,14 @@ int GSM_SFX(launch_spec)(const HostParams& hp, const gsm_step_io& io, int n_step
   ss.actions = rs.actions; ss.obs = rs.obs; ss.nbr_idx = rs.nbr_idx; ss.nbr_feat = rs.nbr_feat;
   ss.nbr_cnt = rs.nbr_cnt; ss.adj = rs.adj; ss.reward = rs.reward; ss.cost = rs.cost;
   ss.done = rs.done; ss.assign = rs.assign;
-#define X(S, n, l, pp) \
-  if (hp.scenario == S && hp.N == n && hp.L == l && P == pp) return launch_spec_one<S, n, l, pp>(kp, n_steps, ss, st);
-  GSM_SPEC_TABLE(X)
-#undef X
-  return -1;
+  const size_t smem = big_smem(hp);
+  auto k = env_big_kernel<GSM_REAL>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k<<<(unsigned)hp.n_envs, kBigThreads, smem, st>>>(kp, n_steps, ss);
+  return (int)cudaGetLastError();
 }
 
 int GSM_SFX(launch_reset)(const HostParams& hp, uint64_t seed, const uint8_t* mask,

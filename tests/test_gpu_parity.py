@@ -116,7 +116,9 @@ def test_f64_25_steps_vs_oracle(name, N, B, kw):
 
 @pytest.mark.parametrize("name,N,P", [("navigation", 3, 8), ("navigation", 3, 4), ("navigation", 3, 2),
                                       ("navigation", 3, 1), ("navigation", 6, 4), ("navigation", 6, 1),
-                                      ("polygon", 6, 4), ("polygon", 6, 1), ("line", 6, 4), ("line", 6, 1)])
+                                      ("polygon", 6, 4), ("polygon", 6, 1), ("line", 6, 4), ("line", 6, 1),
+                                      ("polygon", 3, 1), ("polygon", 5, 1), ("line", 4, 1), ("polygon", 12, 1),
+                                      ("polygon", 12, 2), ("line", 12, 1), ("line", 12, 2), ("navigation", 12, 2)])
 @pytest.mark.parametrize("kw", [{}, {"max_nbrs": 3, "share_reward": True}])
 def test_specialised_kernel_variants_f64(name, N, P, kw, monkeypatch):
     """Every compiled (scenario, N, L, P) instance of the register-resident kernel, single
@@ -141,7 +143,34 @@ def test_specialised_kernel_variants_f64(name, N, P, kw, monkeypatch):
     env.close()
 
 
-@pytest.mark.parametrize("name,N,B,kw", [c for c in CASES if c[1] <= 12])
+@pytest.mark.parametrize("N,K,B,kw", [(24, 16, 9, {}), (48, 32, 5, {"share_reward": True}),
+                                      (96, 32, 3, {"action_mode": "continuous"}), (13, 4, 11, {})])
+def test_large_team_kernel_fused_f64(N, K, B, kw):
+    """env_big_kernel (CTA per env, TMA bulk stores): one fused 10-step launch and single steps
+    against the oracle."""
+    cfg = make_cfg("navigation", N, "f64", max_nbrs=K, **kw)
+    T = 10
+    o = _squeezed_start(cfg, B, 5 + N)
+    s0 = o.agent_state.copy()
+    env = _env(cfg, B)
+    env.set_state(o.agent_state, o.landmark_pos, o.step_count)
+    rng = np.random.default_rng(N)
+    acts = random_actions(cfg, rng, (T, B))
+    wants = [{k: v.copy() for k, v in o.step(acts[t]).items()} for t in range(T)]
+    roll = _np(env.rollout(acts))
+    assert env.kernel_launches == 1                      # fused, not a graph of T launches
+    for t in range(T):
+        assert_match({k: roll[k][t] for k in OUT_KEYS}, wants[t], rtol=F64_RTOL, atol=F64_ATOL,
+                     ctx=f"nav{N} big fused t={t}")
+    np.testing.assert_allclose(env.get_state()[0].cpu().numpy(), o.agent_state, rtol=F64_RTOL, atol=F64_ATOL)
+    env.set_state(s0, o.landmark_pos, np.zeros(B, np.int32))
+    for t in range(2):
+        env.step(acts[t])
+        assert_match(_np(env.buf), wants[t], rtol=F64_RTOL, atol=F64_ATOL, ctx=f"nav{N} big step t={t}")
+    env.close()
+
+
+@pytest.mark.parametrize("name,N,B,kw", [c for c in CASES if c[1] <= 48])
 def test_f32_one_step_within_1e4(name, N, B, kw):
     """Production precision: one step from identical (fp32-representable) states."""
     cfg64 = make_cfg(name, N, "f64", **kw)
