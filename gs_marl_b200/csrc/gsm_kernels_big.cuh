@@ -33,7 +33,7 @@ __host__ __device__ inline BigLayout make_big_layout(int rb, int ent_bytes, int 
   BigLayout b;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += ((bytes + 127) / 128) * 128; return r; };
-  b.off_ent = take((size_t)E * ent_bytes);
+  b.off_ent = take((size_t)((E + 31) / 32 * 32) * ent_bytes);   // padded with far-away dummies
   b.off_vel = take((size_t)N * 2 * rb);
   b.off_nxt = take((size_t)N * 4 * rb);
   b.off_agc = take((size_t)N * 3 * rb);
@@ -90,8 +90,19 @@ env_big_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       q.size = p.size[e]; q.flag = p.eflag[e];
       ent[e] = q;
     }
+    for (int e = E + tid; e < (E + 31) / 32 * 32; e += kBigThreads) {
+      Ent<T> q;                                        // never a neighbour, never in contact
+      q.x = (T)1e30; q.y = (T)1e30; q.size = 0; q.flag = 0;
+      ent[e] = q;
+    }
     for (int i = tid; i < N; i += kBigThreads) {
       agc[3 * i] = p.mass[i]; agc[3 * i + 1] = p.accel[i]; agc[3 * i + 2] = p.max_speed[i];
+    }
+    {                                                  // staging starts as all-padding rows
+      int32_t* z = (int32_t*)(sm + lay.off_stage);
+      const int words = (int)(NW * 2 * lay.stage_bytes / 4), iw = (int)(lay.stage_idx_bytes / 4),
+                sw = (int)(lay.stage_bytes / 4);
+      for (int k = tid; k < words; k += kBigThreads) z[k] = (k % sw) < iw ? -1 : 0;
     }
     if (warp == 0) {                                  // compact list of colliding entities, ascending
       int n = 0;
@@ -106,7 +117,15 @@ env_big_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   }
   __syncthreads();
   int nc = 0;                                          // number of colliding entities
-  for (int e = 0; e < E; e++) nc += (ent[e].flag & 1);  // small, uniform; avoids another barrier
+  T max_size = 0;
+  for (int e = 0; e < E; e++) {                        // small, uniform; avoids another barrier
+    nc += (ent[e].flag & 1);
+    max_size = ent[e].size > max_size ? ent[e].size : max_size;
+  }
+  // contact distances below the sensing radius: a colliding pair is always a neighbour pair
+  // too, so the fp32 sweep needs only ONE squared-distance pre-check per pair
+  const bool col_in_nb = Prec<T>::kCut && ((T)2 * max_size) * (T)1.0001 < p.Rs;
+  int dirty0 = 0, dirty1 = 0;                          // rows of each staging buffer holding real data
   int t_now = p.t[env];
 
   // pre-check thresholds are a few ulp inclusive; the decision is made on the rounded dist
@@ -192,37 +211,31 @@ env_big_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       const T vx = vel[2 * i], vy = vel[2 * i + 1];
       const int64_t row = env * N + i;
       int cnt = 0, ncol = 0;
-      uint32_t carry = 0;                              // adjacency bit that spills into the next word
-      uint32_t* g_adj = (uint32_t*)((unsigned char*)p.adj + so_adj) + row * W;
-      for (int o0 = 0; o0 < E - 1; o0 += 32) {
-        const int o = o0 + lane;
-        const bool valid = o < E - 1;
-        const int e = o + (o >= i ? 1 : 0);
-        bool nb = false, col = false;
-        T dx = 0, dy = 0, d2 = 0, dmin = 0;
-        int fl = 0;
-        if (valid) {
-          const Ent<T> q = ent[e];
-          dx = q.x - me.x; dy = q.y - me.y; d2 = dx * dx + dy * dy;
-          dmin = me.size + q.size; fl = q.flag;
-          if (Prec<T>::kCut) {
-            nb = d2 < Rs2;                             // refined with the rounded sqrt below
-            col = d2 < dmin * dmin * (T)1.000001;
-          } else {
-            const T dist = A::sqrt(d2);
-            nb = dist < p.Rs; col = dist < dmin;
-          }
-          if (p.own_goal_always && e == N + i) nb = true;
-        }
+      uint32_t myword = 0;                             // lane w keeps adjacency word w
+      for (int e0 = 0; e0 < E; e0 += 32) {             // sweep by ENTITY index: ballot == adjacency word
+        const int e = e0 + lane;
+        const Ent<T> q = ent[e];                       // padded: no bounds check
+        const T dx = q.x - me.x, dy = q.y - me.y;
+        const T d2 = dx * dx + dy * dy;
+        const T dmin = me.size + q.size;
+        const bool goal = p.own_goal_always && e == N + i;
+        bool nb, col;
         T dist = 0;
-        if (nb || col) {
-          dist = A::sqrt(d2);
-          if (Prec<T>::kCut) {                         // same predicate as every other kernel: on dist
-            nb = dist < p.Rs || (p.own_goal_always && e == N + i);
-            col = dist < dmin;
+        if (Prec<T>::kCut) {
+          nb = (d2 < Rs2 && e != i) || goal;
+          col = col_in_nb ? nb : (d2 < dmin * dmin * (T)1.000001 && e != i);
+          if (__ballot_sync(FULL, nb || col) == 0u) continue;      // warp-uniform: nothing near
+          if (nb || col) {                             // decide on the rounded distance, like every kernel
+            dist = A::sqrt(d2);
+            nb = (dist < p.Rs && e != i) || goal;
+            col = dist < dmin && e != i;
           }
-          col = col && (e < N || (p.cost_obstacles && (fl >> 1) == GSM_ENT_OBSTACLE));
+        } else {
+          dist = A::sqrt(d2);
+          nb = (dist < p.Rs && e != i && e < E) || goal;
+          col = dist < dmin && e != i && e < E;
         }
+        col = col && (e < N || (p.cost_obstacles && (q.flag >> 1) == GSM_ENT_OBSTACLE));
         const unsigned bits = __ballot_sync(FULL, nb);
         const unsigned cbits = __ballot_sync(FULL, col);
         if (nb) {
@@ -232,22 +245,23 @@ env_big_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
             T evx = 0, evy = 0;
             if (e < N) { evx = vel[2 * e]; evy = vel[2 * e + 1]; }
             T* f = st_feat + pos * GSM_NBR_FEAT_DIM;
-            f[0] = dx; f[1] = dy; f[2] = evx - vx; f[3] = evy - vy; f[4] = dist; f[5] = (T)(fl >> 1);
+            f[0] = dx; f[1] = dy; f[2] = evx - vx; f[3] = evy - vy; f[4] = dist; f[5] = (T)(q.flag >> 1);
           }
         }
         cnt += __popc(bits);
         ncol += __popc(cbits);
-        // others o < i keep their bit position, o >= i move up by one (my own bit stays 0)
-        const uint32_t below = (i > o0) ? low_mask(i - o0 > 32 ? 32 : i - o0) : 0u;
-        const uint32_t lo = bits & below, hi = bits & ~below;
-        const uint32_t word = carry | lo | (hi << 1);
-        carry = hi >> 31;
-        if (lane == 0) g_adj[o0 >> 5] = word;
+        if (lane == (e0 >> 5)) myword = bits;
       }
-      if (lane == 0 && ((E - 1 + 31) >> 5) < W) g_adj[W - 1] = carry;
+      if (lane < W) ((uint32_t*)((unsigned char*)p.adj + so_adj))[row * W + lane] = myword;
       if (cnt > K) cnt = K;
-      for (int k = cnt + lane; k < K; k += 32) st_idx[k] = -1;
-      for (int q = cnt * GSM_NBR_FEAT_DIM + lane; q < K * GSM_NBR_FEAT_DIM; q += 32) st_feat[q] = (T)0;
+      // rows behind the neighbours must read as padding: only rows a previous use of this buffer
+      // filled (dirty) and this agent did not overwrite need clearing
+      {
+        const int hi = (it & 1) ? dirty1 : dirty0;
+        for (int k = cnt + lane; k < hi; k += 32) st_idx[k] = -1;
+        for (int q = cnt * GSM_NBR_FEAT_DIM + lane; q < hi * GSM_NBR_FEAT_DIM; q += 32) st_feat[q] = (T)0;
+        if (it & 1) dirty1 = cnt; else dirty0 = cnt;
+      }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {

@@ -60,8 +60,15 @@ template <> struct AdjBits<0> { typedef uint32_t type; };
 // real env compute on a clamped env index and only their stores are predicated off.
 // OBS = true: observe only (reset path) — no physics, no reward/cost/done, one "step",
 // optional per-env mask (p.mask); the state is not written back.
+// Resident CTAs per SM the compiler must allow for.  The fp32 navigation-3 instances get 7
+// (<= 72 registers -> 28 warps/SM): at the bench batch of 16384 envs (55.4 warps per SM) that
+// is two full rounds of warps instead of 2.3 rounds at 24 warps/SM (ncu_r1_v6: 80 registers).
+template <typename T, int N, int P> struct SpecMinBlocks {
+  static constexpr int value = (sizeof(T) == 4 && N == 3 && (P == 4 || P == 8)) ? 7 : 1;
+};
+
 template <typename T, int SCN, int N, int L, int P, bool OBS>
-__global__ void __launch_bounds__(kSpecThreads)
+__global__ void __launch_bounds__(kSpecThreads, SpecMinBlocks<T, N, P>::value)
 env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
                  const __grid_constant__ StepStrides ss) {
   constexpr int E = N + L, M = E - 1, LPE = N * P, EPW = 32 / LPE;

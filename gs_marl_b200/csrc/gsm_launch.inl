@@ -42,7 +42,8 @@ int GSM_SFX(plan)(const HostParams& hp, LaunchPlan* plan) {
   plan->grid = (hp.n_envs + plan->envs_per_cta - 1) / plan->envs_per_cta;
   if (plan->smem > 227 * 1024) return (int)cudaErrorInvalidValue;
   plan->spec = has_spec(hp) ? 1 : 0;
-  plan->big = (!plan->spec && has_big(hp)) ? 1 : 0;
+  plan->big = ((!plan->spec || env_int("GSM_BIG_MIN_N", 13) <= hp.N) && has_big(hp)) ? 1 : 0;
+  if (plan->big) plan->spec = 0;
   return 0;
 }
 
@@ -195,7 +196,8 @@ static size_t big_smem(const HostParams& hp) {
 static bool has_big(const HostParams& hp) {
   if (env_int("GSM_NO_BIG", 0) != 0 || env_int("GSM_FORCE_P", 0) != 0 || env_int("GSM_FORCE_CTA_ENV", -1) >= 0)
     return false;
-  return hp.scenario == GSM_SCN_NAVIGATION && hp.N > 12 && hp.K % 4 == 0 && big_smem(hp) <= 200 * 1024;
+  return hp.scenario == GSM_SCN_NAVIGATION && hp.N >= env_int("GSM_BIG_MIN_N", 13) && hp.K % 4 == 0 &&
+         big_smem(hp) <= 200 * 1024;
 }
 
 int GSM_SFX(launch_big)(const HostParams& hp, const gsm_step_io& io, int n_steps,

@@ -23,9 +23,13 @@ class BaseScenario:
     def _common(n_agents, n_landmarks, dtype, action_mode, max_nbrs, episode_length,
                 sensing_radius, share_reward, cost_obstacles, own_goal_always):
         E = n_agents + n_landmarks
+        if max_nbrs is None:
+            # [DECL] default padded row count: every other entity for small teams, else capped at
+            # 32 and kept a multiple of 4 (16-byte TMA bulk-store granularity of the row blocks)
+            max_nbrs = E - 1 if E - 1 <= 8 else min(32, (E - 1) // 4 * 4)
         return dict(
             dtype=dtype, action_mode=action_mode, n_agents=n_agents, n_landmarks=n_landmarks,
-            max_nbrs=(E - 1 if max_nbrs is None else max_nbrs), episode_length=episode_length,
+            max_nbrs=max_nbrs, episode_length=episode_length,
             share_reward=share_reward, cost_obstacles=cost_obstacles,
             own_goal_always=own_goal_always,
             sensing_radius=(P.unverified_sensing_radius(n_agents) if sensing_radius is None

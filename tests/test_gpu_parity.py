@@ -370,3 +370,80 @@ def test_full_size_properties_config1():
     assert got["cost"].sum() >= 0 and (got["nbr_cnt"] == np.minimum(8, [[bin(int(w)).count("1") for w in r] for r in adj])).all()
     O.set_threads(1)
     env.close()
+
+
+# ---- edge cases through the raw C ABI ------------------------------------------------------
+def test_out_of_range_actions_mean_no_control():
+    """SPEC §2: a discrete index outside the table is u = 0 (both kernels, both precisions)."""
+    from oracle import gsm_oracle as O
+    for name, N in (("navigation", 3), ("navigation", 24)):
+        cfg = make_cfg(name, N, "f64")
+        B = 19
+        o = _squeezed_start(cfg, B, 4)
+        env = _env(cfg, B)
+        env.set_state(o.agent_state, o.landmark_pos, o.step_count)
+        a = np.random.default_rng(0).integers(-3, 9, (B, N)).astype(np.int32)    # many invalid
+        want = o.step(a)
+        env.step(a)
+        assert_match(_np(env.buf), want, rtol=F64_RTOL, atol=F64_ATOL, ctx=f"{name}{N} bad actions")
+        env.close()
+
+
+@pytest.mark.parametrize("name,N", [("navigation", 3), ("polygon", 6), ("navigation", 24)])
+def test_null_outputs_are_skipped_and_single_env(name, N):
+    """Any output pointer may be NULL; n_envs = 1; raw ctypes call without the Python mirror."""
+    from oracle import gsm_oracle as O
+    lib = abi.load_library()
+    cfg = make_cfg(name, N, "f64")
+    o = _squeezed_start(cfg, 1, 8)
+    c, keep = cfg.to_c()
+    h = C.c_void_p()
+    assert lib.gsm_create(C.byref(c), 1, 0, 0, C.byref(h)) == 0
+    ag = torch.as_tensor(o.agent_state).cuda()
+    lm = torch.as_tensor(o.landmark_pos).cuda()
+    tt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.gsm_set_state(h, ag.data_ptr(), lm.data_ptr(), tt.data_ptr(), st) == 0
+    a_np = random_actions(cfg, np.random.default_rng(1), (1,))
+    a = torch.as_tensor(a_np).cuda()
+    obs = torch.zeros((1, N, 6), dtype=torch.float64, device="cuda")
+    cost = torch.full((1, N), -5.0, dtype=torch.float64, device="cuda")
+    io = abi.GsmStepIO()
+    io.actions, io.obs, io.cost = a.data_ptr(), obs.data_ptr(), cost.data_ptr()   # everything else NULL
+    assert lib.gsm_step(h, C.byref(io), st) == 0, lib.gsm_last_error(h)
+    torch.cuda.synchronize()
+    want = o.step(a_np)
+    np.testing.assert_allclose(obs.cpu().numpy(), want["obs"], rtol=F64_RTOL, atol=F64_ATOL)
+    assert (cost.cpu().numpy() == want["cost"]).all()
+    io2 = abi.GsmStepIO()                                  # actions missing -> error, not a crash
+    assert lib.gsm_step(h, C.byref(io2), st) == -1
+    assert b"actions" in lib.gsm_last_error(h)
+    assert lib.gsm_destroy(h) == 0
+
+
+def test_host_path_with_caller_owned_buffers_and_lsa_zero_problems():
+    """gsm_step_host into plain (pageable) numpy buffers, not the pinned arena."""
+    from oracle import gsm_oracle as O
+    lib = abi.load_library()
+    cfg = make_cfg("line", 5, "f64")
+    B = 21
+    o = _squeezed_start(cfg, B, 2)
+    c, keep = cfg.to_c()
+    h = C.c_void_p()
+    assert lib.gsm_create(C.byref(c), B, 0, 0, C.byref(h)) == 0
+    assert lib.gsm_set_state_host(h, o.agent_state.ctypes.data, o.landmark_pos.ctypes.data,
+                                  o.step_count.ctypes.data) == 0
+    bufs = {k: np.zeros(s, d) for k, (d, s) in cfg.io_shapes(B).items()}
+    bufs["actions"][...] = random_actions(cfg, np.random.default_rng(3), (B,))
+    io = abi.GsmStepIO()
+    for k in abi.GsmStepIO.FIELDS:
+        setattr(io, k, bufs[k].ctypes.data)
+    assert lib.gsm_step_host(h, C.byref(io)) == 0, lib.gsm_last_error(h)
+    want = o.step(bufs["actions"])
+    assert_match(bufs, want, rtol=F64_RTOL, atol=F64_ATOL, ctx="host caller-owned")
+    sz = abi.GsmIoSizes()
+    assert lib.gsm_get_io_sizes(h, C.byref(sz)) == 0
+    assert sz.nbr_feat == bufs["nbr_feat"].nbytes and sz.adj_words == 1 and sz.real_bytes == 8
+    assert lib.gsm_destroy(h) == 0
+    assert lib.gsm_lsa(bufs["obs"].ctypes.data, bufs["assign"].ctypes.data, 0, 4, abi.GSM_F64, 0, None) == 0
+    assert lib.gsm_lsa(None, None, 1, 4, abi.GSM_F64, 0, None) == -1
