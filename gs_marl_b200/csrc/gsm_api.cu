@@ -192,6 +192,9 @@ int do_steps(gsm_env* h, const gsm_step_io& io, int n_steps, cudaStream_t st, in
   if (h->plan.spec)
     e = is_f32(h) ? gsm::launch_spec_f32(h->hp, io, n_steps, rs, observe, mask, mask_stride, st)
                   : gsm::launch_spec_f64(h->hp, io, n_steps, rs, observe, mask, mask_stride, st);
+  else if (h->plan.lane && !observe)
+    e = is_f32(h) ? gsm::launch_lane_f32(h->hp, io, n_steps, rs, st)
+                  : gsm::launch_lane_f64(h->hp, io, n_steps, rs, st);
   else if (h->plan.big && !observe)
     e = is_f32(h) ? gsm::launch_big_f32(h->hp, io, n_steps, rs, st)
                   : gsm::launch_big_f64(h->hp, io, n_steps, rs, st);
@@ -201,7 +204,7 @@ int do_steps(gsm_env* h, const gsm_step_io& io, int n_steps, cudaStream_t st, in
 }
 
 int do_step(gsm_env* h, const gsm_step_io& io, cudaStream_t st) {
-  if (h->plan.spec || h->plan.big) {
+  if (h->plan.spec || h->plan.big || h->plan.lane) {
     const int r = do_steps(h, io, 1, st);
     if (r != -1000) return r;
   }
@@ -425,7 +428,7 @@ int gsm_rollout(gsm_env* h, int32_t n_steps, const gsm_step_io* io, void* stream
   if (!h || !io || n_steps < 1) return GSM_ERR_INVALID_ARG;
   if (!io->actions) return fail(h, GSM_ERR_INVALID_ARG, "io.actions is NULL");
   DeviceGuard guard(h->device);
-  if (h->plan.spec || h->plan.big) {   // fused: all n_steps in one launch, state stays on chip
+  if (h->plan.spec || h->plan.big || h->plan.lane) {   // fused: all n_steps in one launch, state stays on chip
     const int r = do_steps(h, *io, n_steps, (cudaStream_t)stream);
     if (r != -1000) return r;
   }

@@ -35,6 +35,7 @@ struct LaunchPlan {     // chosen once per handle
   int64_t grid;
   int spec;             // 1: a size-specialised register-resident kernel exists (gsm_kernels_spec.cuh)
   int big;              // 1: the large-team CTA-per-env kernel applies (gsm_kernels_big.cuh)
+  int lane;             // 1: the lane-per-agent kernel applies (gsm_kernels_lane.cuh)
 };
 
 // Each returns a cudaError_t (as int).  physics: 1 = full step, 0 = observe only.
@@ -58,6 +59,11 @@ int launch_big_f32(const HostParams& hp, const gsm_step_io& io, int n_steps,
                    const RolloutStrides& rs, cudaStream_t st);
 int launch_big_f64(const HostParams& hp, const gsm_step_io& io, int n_steps,
                    const RolloutStrides& rs, cudaStream_t st);
+// Lane-per-agent navigation kernel (n_steps fused); returns -1 if it does not apply.
+int launch_lane_f32(const HostParams& hp, const gsm_step_io& io, int n_steps,
+                    const RolloutStrides& rs, cudaStream_t st);
+int launch_lane_f64(const HostParams& hp, const gsm_step_io& io, int n_steps,
+                    const RolloutStrides& rs, cudaStream_t st);
 int launch_reset_f32(const HostParams& hp, uint64_t seed, const uint8_t* mask, int64_t mask_stride,
                      cudaStream_t st);
 int launch_reset_f64(const HostParams& hp, uint64_t seed, const uint8_t* mask, int64_t mask_stride,

@@ -1,5 +1,6 @@
 // Production precision (fp32).  FMA contraction allowed.
 #include "gsm_kernels_big.cuh"
+#include "gsm_kernels_lane.cuh"
 #define GSM_REAL float
 #define GSM_SFX(name) name##_f32
 #include "gsm_launch.inl"

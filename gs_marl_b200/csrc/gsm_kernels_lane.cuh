@@ -1,0 +1,251 @@
+// gsm_kernels_lane.cuh — lane-per-agent navigation kernel for medium and large teams
+// (N >= 12 when no better-fitting instance exists), SPEC.md §2-4, §6-7.
+//
+// Issue-efficient mapping for teams whose pair count is too large for one (agent, other)
+// pair per lane: ONE LANE OWNS ONE AGENT and sweeps the other entities sequentially from a
+// shared-memory entity table {x, y, size, flags} (16-byte broadcast loads).  Every issued
+// instruction works for up to 32 agents, there is no per-chunk ballot/popc/branch overhead,
+// and the pair loops carry no dependency except two accumulators, so they pipeline.
+//   N <= 32 : a warp holds floor(32/N) whole envs, phases are separated by __syncwarp;
+//   N  > 32 : one CTA per env, ceil(N/32) warps, phases separated by __syncthreads.
+// The env state stays in shared memory / registers for `n_steps` fused steps.  fp32 uses a
+// squared-distance pre-check so sqrt/softplus run only for pairs in or near contact or within
+// sensing range; fp64 evaluates every pair exactly as SPEC.md writes it.  A found neighbour
+// row goes straight to HBM; the padding behind it is written as 16-byte zero stores.
+#pragma once
+#include "gsm_kernels_spec.cuh"
+
+namespace gsm {
+
+template <typename T> struct LaneEnt { T x, y, size; int flag; int pad_; };
+template <> struct LaneEnt<float> { float x, y, size; int flag; };
+
+struct LaneGeom {        // host-chosen launch geometry
+  int envs_per_warp;     // N <= 32: floor(32 / N); else 0
+  int warps_per_env;     // N > 32: ceil(N / 32); else 0
+  int warps_per_cta;
+  int envs_per_cta;
+};
+__host__ __device__ inline LaneGeom lane_geom(int N) {
+  LaneGeom g;
+  if (N <= 32) { g.envs_per_warp = 32 / N; g.warps_per_env = 0; g.warps_per_cta = 4; g.envs_per_cta = g.envs_per_warp * 4; }
+  else { g.envs_per_warp = 0; g.warps_per_env = (N + 31) / 32; g.warps_per_cta = g.warps_per_env; g.envs_per_cta = 1; }
+  return g;
+}
+__host__ __device__ inline size_t lane_smem(int ent_bytes, int rb, int N, int E, int envs_per_cta) {
+  // per env: entity table, agent velocities, shared-reward scratch; per CTA: collider list
+  size_t per_env = ((size_t)E * ent_bytes + 15) / 16 * 16 + ((size_t)N * 2 * rb + 15) / 16 * 16 +
+                   ((size_t)N * rb + 15) / 16 * 16;
+  return per_env * envs_per_cta + ((size_t)E * 4 + 15) / 16 * 16;
+}
+
+template <typename T> __device__ __forceinline__ void st_zero16(void* p) {
+  *reinterpret_cast<int4*>(p) = make_int4(0, 0, 0, 0);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
+                const __grid_constant__ StepStrides ss) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  typedef Arith<T> A;
+  typedef LaneEnt<T> EntT;
+  const int N = p.N, L = p.L, E = p.E, K = p.K, W = p.W;
+  const LaneGeom g = lane_geom(N);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool multi = N > 32;                           // env spans the whole CTA
+
+  // ---- which env / agent am I ---------------------------------------------------------------
+  int env_l, i;                                        // env slot in the CTA, my agent
+  if (multi) { env_l = 0; i = tid; }
+  else { const int eiw = lane / N; env_l = warp * g.envs_per_warp + eiw; i = lane - eiw * N; }
+  const int64_t env_raw = (int64_t)blockIdx.x * g.envs_per_cta + env_l;
+  const bool has_env = env_raw < p.n_envs && (multi || lane < g.envs_per_warp * N);
+  const bool active = has_env && i < N;                // lanes without an agent idle (never store)
+  const int64_t env = has_env ? env_raw : 0;
+
+  const size_t ent_b = ((size_t)E * sizeof(EntT) + 15) / 16 * 16, vel_b = ((size_t)N * 2 * sizeof(T) + 15) / 16 * 16,
+               rew_b = ((size_t)N * sizeof(T) + 15) / 16 * 16;
+  unsigned char* base = sm + (size_t)(has_env || multi ? env_l : 0) * (ent_b + vel_b + rew_b);
+  EntT* ent = (EntT*)base;
+  T* vel = (T*)(base + ent_b);
+  T* rew = (T*)(base + ent_b + vel_b);
+  int* clist = (int*)(sm + (size_t)g.envs_per_cta * (ent_b + vel_b + rew_b));
+
+  // ---- stage: entity tables (each env by its own lanes / CTA), collider list ------------------
+  {
+    const T* g_ag = p.agent_state + env * N * 4;
+    const T* g_lm = p.lm_pos + env * L * 2;
+    const int nl = multi ? blockDim.x : N, me = multi ? tid : i;     // lanes cooperating on this env
+    if (has_env || multi) {
+      for (int e = me; e < E; e += nl) {
+        EntT q;
+        if (e < N) { q.x = g_ag[4 * e]; q.y = g_ag[4 * e + 1]; vel[2 * e] = g_ag[4 * e + 2]; vel[2 * e + 1] = g_ag[4 * e + 3]; }
+        else { q.x = g_lm[2 * (e - N)]; q.y = g_lm[2 * (e - N) + 1]; }
+        q.size = p.size[e]; q.flag = p.eflag[e];
+        ent[e] = q;
+      }
+    }
+    if (warp == 0) {
+      int n = 0;
+      for (int e0 = 0; e0 < E; e0 += 32) {
+        const int e = e0 + lane;
+        const bool c = e < E && (p.eflag[e] & 1);
+        const unsigned b = __ballot_sync(0xffffffffu, c);
+        if (c) clist[n + __popc(b & low_mask(lane))] = e;
+        n += __popc(b);
+      }
+    }
+  }
+  __syncthreads();
+  int nc = 0;
+  for (int e = 0; e < E; e++) nc += (p.eflag[e] & 1);
+
+  const int ii = active ? i : 0;
+  T px = ent[ii].x, py = ent[ii].y, vx = vel[2 * ii], vy = vel[2 * ii + 1];
+  const T size_i = ent[ii].size;
+  const bool coll_i = ent[ii].flag & 1;
+  const T mass_i = p.mass[ii], accel_i = p.accel[ii], maxsp_i = p.max_speed[ii];
+  const T gxl = ent[N + ii].x, gyl = ent[N + ii].y;    // own goal (static)
+  int t_now = p.t[env];
+  const T Rs2 = p.Rs * p.Rs * (T)1.000001;             // pre-checks a few ulp inclusive
+  const T cut = (T)kFarCut * p.km;
+  const int64_t row = env * N + ii;
+
+  // output cursors of my agent
+  const unsigned char* c_act = (const unsigned char*)p.actions +
+      (p.action_mode == GSM_ACT_DISCRETE ? row * 4 : row * 2 * (int64_t)sizeof(T));
+  unsigned char* c_idx = (unsigned char*)(p.nbr_idx + row * K);
+  unsigned char* c_feat = (unsigned char*)(p.nbr_feat + row * K * GSM_NBR_FEAT_DIM);
+  unsigned char* c_obs = (unsigned char*)(p.obs + row * GSM_OBS_DIM);
+  unsigned char* c_cnt = (unsigned char*)(p.nbr_cnt + row);
+  unsigned char* c_adj = (unsigned char*)(p.adj + row * W);
+  unsigned char* c_rew = (unsigned char*)(p.reward + row);
+  unsigned char* c_cost = (unsigned char*)(p.cost + row);
+  unsigned char* c_done = (unsigned char*)(p.done + row);
+  unsigned char* c_asg = (unsigned char*)(p.assign + row);
+
+  for (int step = 0; step < n_steps; step++) {
+    // ---- SPEC §2-3: forces (entity table = state at the start of the step) --------------------
+    T fx = 0, fy = 0;
+    if (active) {
+      T ux = 0, uy = 0;
+      if (p.action_mode == GSM_ACT_DISCRETE) {
+        const int a = *(const int32_t*)c_act;
+        if (a >= 0 && a < p.n_actions) { ux = p.discrete_u[a][0]; uy = p.discrete_u[a][1]; }
+      } else { ux = ((const T*)c_act)[0]; uy = ((const T*)c_act)[1]; }
+      fx = accel_i * ux; fy = accel_i * uy;
+      if (coll_i) {
+        for (int c = 0; c < nc; c++) {
+          const int j = clist[c];
+          const EntT q = ent[j];
+          const T dx = px - q.x, dy = py - q.y;
+          const T d2 = dx * dx + dy * dy;
+          const T dmin = size_i + q.size;
+          if (Prec<T>::kCut) {                         // fp32: x < -kFarCut <=> dist > dmin + cut
+            const T far = dmin + cut;
+            if (d2 > far * far || j == i) continue;
+          } else if (j == i) continue;
+          const T dist = A::sqrt(d2);
+          const T x = A::div_const(-(dist - dmin), p.km, p.km_inv);
+          if (Prec<T>::kCut && x < (T)(-kFarCut)) continue;
+          const T pen = softplus(x) * p.km;
+          fx = fx + A::div(p.cf * dx, dist) * pen;
+          fy = fy + A::div(p.cf * dy, dist) * pen;
+        }
+      }
+      // ---- SPEC §4 ------------------------------------------------------------------------------
+      vx = vx * p.one_minus_damp; vy = vy * p.one_minus_damp;
+      vx = vx + A::div(fx, mass_i) * p.dt;
+      vy = vy + A::div(fy, mass_i) * p.dt;
+      if (maxsp_i > (T)0) {
+        const T sp = A::sqrt(vx * vx + vy * vy);
+        if (sp > maxsp_i) { vx = A::div(vx, sp) * maxsp_i; vy = A::div(vy, sp) * maxsp_i; }
+      }
+      px = px + vx * p.dt; py = py + vy * p.dt;
+    }
+    t_now += 1;
+    if (multi) __syncthreads(); else __syncwarp();     // everyone has read the old table
+    if (active) { ent[i].x = px; ent[i].y = py; vel[2 * i] = vx; vel[2 * i + 1] = vy; }
+    if (multi) __syncthreads(); else __syncwarp();
+
+    // ---- SPEC §6-7: neighbour graph on the new table --------------------------------------------
+    int cnt = 0, ncol = 0;
+    T r = 0;
+    if (active) {
+      uint32_t word = 0;
+      for (int e = 0; e < E; e++) {
+        const EntT q = ent[e];
+        const T dx = q.x - px, dy = q.y - py;
+        const T d2 = dx * dx + dy * dy;
+        const T dmin = size_i + q.size;
+        const bool goal = p.own_goal_always && e == N + i;
+        bool near;
+        if (Prec<T>::kCut) near = (d2 < Rs2 || d2 < dmin * dmin * (T)1.000001 || goal) && e != i;
+        else near = e != i;
+        if (near) {
+          const T dist = A::sqrt(d2);
+          const bool nb = dist < p.Rs || goal;
+          if (dist < dmin && (e < N || (p.cost_obstacles && (q.flag >> 1) == GSM_ENT_OBSTACLE))) ncol++;
+          if (nb) {
+            word |= 1u << (e & 31);
+            if (cnt < K) {
+              ((int32_t*)c_idx)[cnt] = e;
+              T evx = 0, evy = 0;
+              if (e < N) { evx = vel[2 * e]; evy = vel[2 * e + 1]; }
+              T* f = (T*)c_feat + cnt * GSM_NBR_FEAT_DIM;
+              st2<T>(f, dx, dy); st2<T>(f + 2, evx - vx, evy - vy); st2<T>(f + 4, dist, (T)(q.flag >> 1));
+            }
+            cnt++;
+          }
+        }
+        if ((e & 31) == 31 || e == E - 1) { ((uint32_t*)c_adj)[e >> 5] = word; word = 0; }
+      }
+      if (cnt > K) cnt = K;
+      // padding rows: -1 / zeros from the first free row to the end of my block, widest stores
+      {
+        unsigned char* q = c_idx + (size_t)cnt * 4;
+        unsigned char* end = c_idx + (size_t)K * 4;
+        while (q < end && ((uintptr_t)q & 15)) { *(int32_t*)q = -1; q += 4; }
+        for (; q + 16 <= end; q += 16) *reinterpret_cast<int4*>(q) = make_int4(-1, -1, -1, -1);
+        for (; q < end; q += 4) *(int32_t*)q = -1;
+        q = c_feat + (size_t)cnt * GSM_NBR_FEAT_DIM * sizeof(T);
+        end = c_feat + (size_t)K * GSM_NBR_FEAT_DIM * sizeof(T);
+        while (q < end && ((uintptr_t)q & 15)) { *(T*)q = (T)0; q += sizeof(T); }
+        for (; q + 16 <= end; q += 16) st_zero16<T>(q);
+        for (; q < end; q += sizeof(T)) *(T*)q = (T)0;
+      }
+      const T gx = gxl - px, gy = gyl - py;
+      const T d = A::sqrt(gx * gx + gy * gy);
+      r = ((T)0 - p.w_dist * d) + (d < p.goal_tol ? p.w_goal : (T)0);
+      T* o = (T*)c_obs;
+      st2<T>(o, vx, vy); st2<T>(o + 2, px, py); st2<T>(o + 4, gx, gy);
+      *(int32_t*)c_cnt = cnt;
+      *(T*)c_cost = (T)ncol;
+      *c_done = (uint8_t)(t_now >= p.episode_length);
+      *(int32_t*)c_asg = i;
+      if (!p.share_reward) *(T*)c_rew = r;
+    }
+    if (p.share_reward) {                              // mean over the env's agents, ascending order
+      if (active) rew[i] = r;
+      if (multi) __syncthreads(); else __syncwarp();
+      if (active) {
+        T s = rew[0];
+        for (int k = 1; k < N; k++) s = s + rew[k];
+        *(T*)c_rew = s / (T)N;
+      }
+      if (multi) __syncthreads(); else __syncwarp();
+    }
+    c_act += ss.actions; c_idx += ss.nbr_idx; c_feat += ss.nbr_feat; c_obs += ss.obs;
+    c_cnt += ss.nbr_cnt; c_adj += ss.adj; c_rew += ss.reward; c_cost += ss.cost;
+    c_done += ss.done; c_asg += ss.assign;
+  }
+
+  if (active) {
+    T* a = p.agent_state + row * 4;
+    st2<T>(a, px, py); st2<T>(a + 2, vx, vy);
+    if (i == 0) p.t[env] = t_now;
+  }
+}
+
+}  // namespace gsm

@@ -12,6 +12,7 @@ static int env_int(const char* name, int dflt) {
 
 static bool has_spec(const HostParams& hp);
 static bool has_big(const HostParams& hp);
+static bool has_lane(const HostParams& hp);
 static int next_pow2(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
 int GSM_SFX(plan)(const HostParams& hp, LaunchPlan* plan) {
@@ -42,7 +43,10 @@ int GSM_SFX(plan)(const HostParams& hp, LaunchPlan* plan) {
   plan->grid = (hp.n_envs + plan->envs_per_cta - 1) / plan->envs_per_cta;
   if (plan->smem > 227 * 1024) return (int)cudaErrorInvalidValue;
   plan->spec = has_spec(hp) ? 1 : 0;
-  plan->big = ((!plan->spec || env_int("GSM_BIG_MIN_N", 13) <= hp.N) && has_big(hp)) ? 1 : 0;
+  // preference: lane-per-agent (N >= GSM_LANE_MIN_N) > specialised > CTA-per-env > generic
+  plan->lane = has_lane(hp) ? 1 : 0;
+  if (plan->lane) plan->spec = 0;
+  plan->big = (!plan->lane && (!plan->spec || env_int("GSM_BIG_MIN_N", 13) <= hp.N) && has_big(hp)) ? 1 : 0;
   if (plan->big) plan->spec = 0;
   return 0;
 }
@@ -217,6 +221,37 @@ int GSM_SFX(launch_big)(const HostParams& hp, const gsm_step_io& io, int n_steps
     if (e != cudaSuccess) return (int)e;
   }
   k<<<(unsigned)hp.n_envs, kBigThreads, smem, st>>>(kp, n_steps, ss);
+  return (int)cudaGetLastError();
+}
+
+// ---- lane-per-agent kernel (gsm_kernels_lane.cuh) ----------------------------------------------
+static bool has_lane(const HostParams& hp) {
+  if (env_int("GSM_NO_LANE", 0) != 0 || env_int("GSM_FORCE_P", 0) != 0 || env_int("GSM_FORCE_CTA_ENV", -1) >= 0)
+    return false;
+  if (env_int("GSM_SPEC_P", 0) != 0 && spec_P(hp) != 0) return false;   // an explicit spec variant was asked for
+  return hp.scenario == GSM_SCN_NAVIGATION && hp.N >= env_int("GSM_LANE_MIN_N", 13) && hp.N <= 128;
+}
+
+int GSM_SFX(launch_lane)(const HostParams& hp, const gsm_step_io& io, int n_steps,
+                         const RolloutStrides& rs, cudaStream_t st) {
+  if (!has_lane(hp)) return -1;
+  if (hp.n_envs == 0) return 0;
+  KParams<GSM_REAL> kp;
+  fill_kparams(kp, hp, io, 0, nullptr, 0);
+  StepStrides ss;
+  ss.actions = rs.actions; ss.obs = rs.obs; ss.nbr_idx = rs.nbr_idx; ss.nbr_feat = rs.nbr_feat;
+  ss.nbr_cnt = rs.nbr_cnt; ss.adj = rs.adj; ss.reward = rs.reward; ss.cost = rs.cost;
+  ss.done = rs.done; ss.assign = rs.assign;
+  const LaneGeom g = lane_geom(hp.N);
+  const size_t smem = lane_smem((int)sizeof(LaneEnt<GSM_REAL>), (int)sizeof(GSM_REAL), hp.N, hp.N + hp.L,
+                                g.envs_per_cta);
+  auto k = env_lane_kernel<GSM_REAL>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int64_t grid = (hp.n_envs + g.envs_per_cta - 1) / g.envs_per_cta;
+  k<<<(unsigned)grid, g.warps_per_cta * 32, smem, st>>>(kp, n_steps, ss);
   return (int)cudaGetLastError();
 }
 

@@ -143,11 +143,21 @@ def test_specialised_kernel_variants_f64(name, N, P, kw, monkeypatch):
     env.close()
 
 
+@pytest.mark.parametrize("which", ["lane", "big"])
 @pytest.mark.parametrize("N,K,B,kw", [(24, 16, 9, {}), (48, 32, 5, {"share_reward": True}),
-                                      (96, 32, 3, {"action_mode": "continuous"}), (13, 4, 11, {})])
-def test_large_team_kernel_fused_f64(N, K, B, kw):
-    """env_big_kernel (CTA per env, TMA bulk stores): one fused 10-step launch and single steps
-    against the oracle."""
+                                      (96, 32, 3, {"action_mode": "continuous"}), (13, 4, 11, {}),
+                                      (12, 32, 37, {}), (24, 7, 6, {"own_goal_always": False}),
+                                      (33, 64, 4, {"n_obstacles": 0, "cost_obstacles": False})])
+def test_large_team_kernel_fused_f64(N, K, B, kw, which, monkeypatch):
+    """The two large-team kernels — env_lane_kernel (lane per agent) and env_big_kernel (CTA per
+    env, TMA bulk stores): one fused 10-step launch and single steps against the oracle."""
+    if which == "big":
+        monkeypatch.setenv("GSM_NO_LANE", "1")
+        monkeypatch.setenv("GSM_BIG_MIN_N", "12")
+        if K % 4:
+            pytest.skip("bulk stores need K % 4 == 0")
+    else:
+        monkeypatch.setenv("GSM_LANE_MIN_N", "12")
     cfg = make_cfg("navigation", N, "f64", max_nbrs=K, **kw)
     T = 10
     o = _squeezed_start(cfg, B, 5 + N)
