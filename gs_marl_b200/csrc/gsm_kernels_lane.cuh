@@ -11,7 +11,7 @@
 // The env state stays in shared memory / registers for `n_steps` fused steps.  fp32 uses a
 // squared-distance pre-check so sqrt/softplus run only for pairs in or near contact or within
 // sensing range; fp64 evaluates every pair exactly as SPEC.md writes it.  A found neighbour
-// row goes straight to HBM; the padding behind it is written as 16-byte zero stores.
+// row goes straight to HBM over a warp-cooperative, fully coalesced clear of the row blocks.
 #pragma once
 #include "gsm_kernels_spec.cuh"
 
@@ -32,11 +32,18 @@ __host__ __device__ inline LaneGeom lane_geom(int N) {
   else { g.envs_per_warp = 0; g.warps_per_env = (N + 31) / 32; g.warps_per_cta = g.warps_per_env; g.envs_per_cta = 1; }
   return g;
 }
+// Entity tables are padded to a multiple of 8 plus 8 far-away dummies (index lane_epad(E)):
+// the pair sweeps run in fully unrolled groups of 8 without bounds checks.
+__host__ __device__ inline int lane_epad(int E) { return (E + 7) / 8 * 8; }
+__host__ __device__ inline size_t lane_env_bytes(int ent_bytes, int rb, int N, int E) {
+  return ((size_t)(lane_epad(E) + 8) * ent_bytes + 15) / 16 * 16 + ((size_t)N * 2 * rb + 15) / 16 * 16 +
+         ((size_t)N * rb + 15) / 16 * 16;
+}
 __host__ __device__ inline size_t lane_smem(int ent_bytes, int rb, int N, int E, int envs_per_cta) {
   // per env: entity table, agent velocities, shared-reward scratch; per CTA: collider list
-  size_t per_env = ((size_t)E * ent_bytes + 15) / 16 * 16 + ((size_t)N * 2 * rb + 15) / 16 * 16 +
-                   ((size_t)N * rb + 15) / 16 * 16;
-  return per_env * envs_per_cta + ((size_t)E * 4 + 15) / 16 * 16;
+  // (padded to a multiple of 8) and the per-word masks of entities that count for the cost
+  return lane_env_bytes(ent_bytes, rb, N, E) * envs_per_cta + ((size_t)(lane_epad(E) + 8) * 4 + 15) / 16 * 16 +
+         ((size_t)((E + 31) / 32) * 4 + 15) / 16 * 16;
 }
 
 template <typename T> __device__ __forceinline__ void st_zero16(void* p) {
@@ -64,13 +71,15 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   const bool active = has_env && i < N;                // lanes without an agent idle (never store)
   const int64_t env = has_env ? env_raw : 0;
 
-  const size_t ent_b = ((size_t)E * sizeof(EntT) + 15) / 16 * 16, vel_b = ((size_t)N * 2 * sizeof(T) + 15) / 16 * 16,
+  const int EP = lane_epad(E);                         // padded entity count; dummy index = EP
+  const size_t ent_b = ((size_t)(EP + 8) * sizeof(EntT) + 15) / 16 * 16, vel_b = ((size_t)N * 2 * sizeof(T) + 15) / 16 * 16,
                rew_b = ((size_t)N * sizeof(T) + 15) / 16 * 16;
   unsigned char* base = sm + (size_t)(has_env || multi ? env_l : 0) * (ent_b + vel_b + rew_b);
   EntT* ent = (EntT*)base;
   T* vel = (T*)(base + ent_b);
   T* rew = (T*)(base + ent_b + vel_b);
   int* clist = (int*)(sm + (size_t)g.envs_per_cta * (ent_b + vel_b + rew_b));
+  uint32_t* costmask = (uint32_t*)((unsigned char*)clist + ((size_t)(EP + 8) * 4 + 15) / 16 * 16);
 
   // ---- stage: entity tables (each env by its own lanes / CTA), collider list ------------------
   {
@@ -78,11 +87,12 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     const T* g_lm = p.lm_pos + env * L * 2;
     const int nl = multi ? blockDim.x : N, me = multi ? tid : i;     // lanes cooperating on this env
     if (has_env || multi) {
-      for (int e = me; e < E; e += nl) {
+      for (int e = me; e < EP + 8; e += nl) {
         EntT q;
         if (e < N) { q.x = g_ag[4 * e]; q.y = g_ag[4 * e + 1]; vel[2 * e] = g_ag[4 * e + 2]; vel[2 * e + 1] = g_ag[4 * e + 3]; }
-        else { q.x = g_lm[2 * (e - N)]; q.y = g_lm[2 * (e - N) + 1]; }
-        q.size = p.size[e]; q.flag = p.eflag[e];
+        else if (e < E) { q.x = g_lm[2 * (e - N)]; q.y = g_lm[2 * (e - N) + 1]; }
+        else { q.x = (T)1e18; q.y = (T)1e18; }         // dummy: never near anything
+        q.size = e < E ? p.size[e] : (T)0; q.flag = e < E ? (int)p.eflag[e] : 0;
         ent[e] = q;
       }
     }
@@ -90,11 +100,17 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       int n = 0;
       for (int e0 = 0; e0 < E; e0 += 32) {
         const int e = e0 + lane;
-        const bool c = e < E && (p.eflag[e] & 1);
+        const int fl = e < E ? (int)p.eflag[e] : 0;
+        const bool c = fl & 1;
         const unsigned b = __ballot_sync(0xffffffffu, c);
         if (c) clist[n + __popc(b & low_mask(lane))] = e;
         n += __popc(b);
+        // entities whose overlap counts into the cost: agents, and obstacles if configured
+        const bool cc = e < E && (e < N || (p.cost_obstacles && (fl >> 1) == GSM_ENT_OBSTACLE));
+        const unsigned cb = __ballot_sync(0xffffffffu, cc);
+        if (lane == 0) costmask[e0 >> 5] = cb;
       }
+      for (int k = n + lane; k < (n + 7) / 8 * 8; k += 32) clist[k] = EP;   // pad with the dummy
     }
   }
   __syncthreads();
@@ -124,6 +140,8 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   unsigned char* c_cost = (unsigned char*)(p.cost + row);
   unsigned char* c_done = (unsigned char*)(p.done + row);
   unsigned char* c_asg = (unsigned char*)(p.assign + row);
+  unsigned char* c_idx_base = (unsigned char*)p.nbr_idx;   // slot bases for the warp-wide clears
+  unsigned char* c_feat_base = (unsigned char*)p.nbr_feat;
 
   for (int step = 0; step < n_steps; step++) {
     // ---- SPEC §2-3: forces (entity table = state at the start of the step) --------------------
@@ -136,22 +154,39 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       } else { ux = ((const T*)c_act)[0]; uy = ((const T*)c_act)[1]; }
       fx = accel_i * ux; fy = accel_i * uy;
       if (coll_i) {
-        for (int c = 0; c < nc; c++) {
-          const int j = clist[c];
-          const EntT q = ent[j];
-          const T dx = px - q.x, dy = py - q.y;
-          const T d2 = dx * dx + dy * dy;
-          const T dmin = size_i + q.size;
-          if (Prec<T>::kCut) {                         // fp32: x < -kFarCut <=> dist > dmin + cut
-            const T far = dmin + cut;
-            if (d2 > far * far || j == i) continue;
-          } else if (j == i) continue;
-          const T dist = A::sqrt(d2);
-          const T x = A::div_const(-(dist - dmin), p.km, p.km_inv);
-          if (Prec<T>::kCut && x < (T)(-kFarCut)) continue;
-          const T pen = softplus(x) * p.km;
-          fx = fx + A::div(p.cf * dx, dist) * pen;
-          fy = fy + A::div(p.cf * dy, dist) * pen;
+        // per 32-collider block: a branch-free, sqrt-free sweep (unrolled groups of 8 over the padded
+        // list) marks the pairs that can be in contact; only those, in ascending order like SPEC §3,
+        // go through sqrt / softplus.  fp64 marks every pair.
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+          uint32_t cm = 0;
+          for (int g0 = 0; g0 < 32 && c0 + g0 < nc; g0 += 8) {
+            uint32_t m8 = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const int j = clist[c0 + g0 + k];
+              const EntT q = ent[j];
+              const T dx = px - q.x, dy = py - q.y;
+              const T d2 = dx * dx + dy * dy;
+              const T far = size_i + q.size + cut;
+              if (Prec<T>::kCut ? (d2 <= far * far) : (j < E)) m8 |= 1u << k;
+            }
+            cm |= m8 << g0;
+          }
+          while (cm) {
+            const int k = __ffs(cm) - 1;
+            cm &= cm - 1;
+            const int j = clist[c0 + k];
+            if (j == i) continue;
+            const EntT q = ent[j];
+            const T dx = px - q.x, dy = py - q.y;
+            const T dist = A::sqrt(dx * dx + dy * dy);
+            const T dmin = size_i + q.size;
+            const T x = A::div_const(-(dist - dmin), p.km, p.km_inv);
+            if (Prec<T>::kCut && x < (T)(-kFarCut)) continue;
+            const T pen = softplus(x) * p.km;
+            fx = fx + A::div(p.cf * dx, dist) * pen;
+            fy = fy + A::div(p.cf * dy, dist) * pen;
+          }
         }
       }
       // ---- SPEC §4 ------------------------------------------------------------------------------
@@ -169,52 +204,86 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     if (active) { ent[i].x = px; ent[i].y = py; vel[2 * i] = vx; vel[2 * i + 1] = vy; }
     if (multi) __syncthreads(); else __syncwarp();
 
+    // ---- padding first: the rows of this warp's agents are one contiguous region of nbr_idx /
+    // nbr_feat, so the warp clears it with fully coalesced 16-byte stores (-1 / zeros); the few
+    // real neighbour rows are written over it after the __syncwarp.  (Per-lane padding loops cost
+    // L1TEX one line per lane per instruction: ncu_r1_lane24.)
+    {
+      int64_t row0, nrows;
+      if (multi) { row0 = env * N + warp * 32; nrows = N - warp * 32; nrows = nrows > 32 ? 32 : (nrows < 0 ? 0 : nrows); }
+      else {
+        const int64_t envw = (int64_t)blockIdx.x * g.envs_per_cta + warp * g.envs_per_warp;
+        int64_t ne = p.n_envs - envw;
+        ne = ne > g.envs_per_warp ? g.envs_per_warp : (ne < 0 ? 0 : ne);
+        row0 = envw * N; nrows = ne * N;
+      }
+      unsigned char* zi = c_idx_base + row0 * K * 4;
+      const int64_t bi = nrows * K * 4;
+      if ((((uintptr_t)zi | (uintptr_t)bi) & 15) == 0) {
+        for (int64_t q = (int64_t)lane * 16; q < bi; q += 512) *reinterpret_cast<int4*>(zi + q) = make_int4(-1, -1, -1, -1);
+      } else {
+        for (int64_t q = (int64_t)lane * 4; q < bi; q += 128) *reinterpret_cast<int32_t*>(zi + q) = -1;
+      }
+      unsigned char* zf = c_feat_base + row0 * K * GSM_NBR_FEAT_DIM * (int64_t)sizeof(T);
+      const int64_t bf = nrows * K * GSM_NBR_FEAT_DIM * (int64_t)sizeof(T);
+      if ((((uintptr_t)zf | (uintptr_t)bf) & 15) == 0) {
+        for (int64_t q = (int64_t)lane * 16; q < bf; q += 512) st_zero16<T>(zf + q);
+      } else {
+        for (int64_t q = (int64_t)lane * sizeof(T); q < bf; q += 32 * sizeof(T)) *reinterpret_cast<T*>(zf + q) = (T)0;
+      }
+      __syncwarp();
+    }
+
     // ---- SPEC §6-7: neighbour graph on the new table --------------------------------------------
     int cnt = 0, ncol = 0;
     T r = 0;
     if (active) {
-      uint32_t word = 0;
-      for (int e = 0; e < E; e++) {
-        const EntT q = ent[e];
-        const T dx = q.x - px, dy = q.y - py;
-        const T d2 = dx * dx + dy * dy;
-        const T dmin = size_i + q.size;
-        const bool goal = p.own_goal_always && e == N + i;
-        bool near;
-        if (Prec<T>::kCut) near = (d2 < Rs2 || d2 < dmin * dmin * (T)1.000001 || goal) && e != i;
-        else near = e != i;
-        if (near) {
-          const T dist = A::sqrt(d2);
-          const bool nb = dist < p.Rs || goal;
-          if (dist < dmin && (e < N || (p.cost_obstacles && (q.flag >> 1) == GSM_ENT_OBSTACLE))) ncol++;
-          if (nb) {
-            word |= 1u << (e & 31);
+      // per 32-entity block: a branch-free, sqrt-free sweep (unrolled groups of 8 over the padded
+      // table) marks candidates on the squared distance (a few ulp inclusive); the set bits, in
+      // ascending entity order, then decide on the rounded distance like every other kernel,
+      // count collisions and write their rows.  fp64 marks every pair.
+      const int goal_e = p.own_goal_always ? N + i : -1;
+      for (int e0 = 0; e0 < E; e0 += 32) {
+        uint32_t cand = 0;
+        for (int g0 = 0; g0 < 32 && e0 + g0 < E; g0 += 8) {
+          uint32_t m8 = 0;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const EntT q = ent[e0 + g0 + k];
+            const T dx = q.x - px, dy = q.y - py;
+            const T d2 = dx * dx + dy * dy;
+            const T dm = size_i + q.size;
+            if (Prec<T>::kCut ? (d2 < Rs2 || d2 < dm * dm * (T)1.000001) : (e0 + g0 + k < E)) m8 |= 1u << k;
+          }
+          cand |= m8 << g0;
+        }
+        if ((unsigned)(goal_e - e0) < 32u) cand |= 1u << (goal_e - e0);
+        if ((unsigned)(i - e0) < 32u) cand &= ~(1u << (i - e0));
+        const uint32_t cmask = costmask[e0 >> 5];
+        uint32_t word = 0;
+        while (cand) {
+          const int k = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const int e = e0 + k;
+          const EntT q = ent[e];
+          const T dx = q.x - px, dy = q.y - py;
+          const T dist = A::sqrt(dx * dx + dy * dy);
+          if (dist < size_i + q.size && ((cmask >> k) & 1u)) ncol++;
+          if (dist < p.Rs || e == goal_e) {
+            word |= 1u << k;
             if (cnt < K) {
-              ((int32_t*)c_idx)[cnt] = e;
               T evx = 0, evy = 0;
               if (e < N) { evx = vel[2 * e]; evy = vel[2 * e + 1]; }
+              ((int32_t*)c_idx)[cnt] = e;
               T* f = (T*)c_feat + cnt * GSM_NBR_FEAT_DIM;
               st2<T>(f, dx, dy); st2<T>(f + 2, evx - vx, evy - vy); st2<T>(f + 4, dist, (T)(q.flag >> 1));
             }
             cnt++;
           }
         }
-        if ((e & 31) == 31 || e == E - 1) { ((uint32_t*)c_adj)[e >> 5] = word; word = 0; }
+        ((uint32_t*)c_adj)[e0 >> 5] = word;
       }
       if (cnt > K) cnt = K;
-      // padding rows: -1 / zeros from the first free row to the end of my block, widest stores
-      {
-        unsigned char* q = c_idx + (size_t)cnt * 4;
-        unsigned char* end = c_idx + (size_t)K * 4;
-        while (q < end && ((uintptr_t)q & 15)) { *(int32_t*)q = -1; q += 4; }
-        for (; q + 16 <= end; q += 16) *reinterpret_cast<int4*>(q) = make_int4(-1, -1, -1, -1);
-        for (; q < end; q += 4) *(int32_t*)q = -1;
-        q = c_feat + (size_t)cnt * GSM_NBR_FEAT_DIM * sizeof(T);
-        end = c_feat + (size_t)K * GSM_NBR_FEAT_DIM * sizeof(T);
-        while (q < end && ((uintptr_t)q & 15)) { *(T*)q = (T)0; q += sizeof(T); }
-        for (; q + 16 <= end; q += 16) st_zero16<T>(q);
-        for (; q < end; q += sizeof(T)) *(T*)q = (T)0;
-      }
       const T gx = gxl - px, gy = gyl - py;
       const T d = A::sqrt(gx * gx + gy * gy);
       r = ((T)0 - p.w_dist * d) + (d < p.goal_tol ? p.w_goal : (T)0);
@@ -239,6 +308,7 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     c_act += ss.actions; c_idx += ss.nbr_idx; c_feat += ss.nbr_feat; c_obs += ss.obs;
     c_cnt += ss.nbr_cnt; c_adj += ss.adj; c_rew += ss.reward; c_cost += ss.cost;
     c_done += ss.done; c_asg += ss.assign;
+    c_idx_base += ss.nbr_idx; c_feat_base += ss.nbr_feat;
   }
 
   if (active) {
