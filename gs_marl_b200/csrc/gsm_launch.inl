@@ -229,7 +229,7 @@ static bool has_lane(const HostParams& hp) {
   if (env_int("GSM_NO_LANE", 0) != 0 || env_int("GSM_FORCE_P", 0) != 0 || env_int("GSM_FORCE_CTA_ENV", -1) >= 0)
     return false;
   if (env_int("GSM_SPEC_P", 0) != 0 && spec_P(hp) != 0) return false;   // an explicit spec variant was asked for
-  return hp.scenario == GSM_SCN_NAVIGATION && hp.N >= env_int("GSM_LANE_MIN_N", 13) && hp.N <= 128;
+  return hp.scenario == GSM_SCN_NAVIGATION && hp.N >= env_int("GSM_LANE_MIN_N", 6) && hp.N <= 128;
 }
 
 int GSM_SFX(launch_lane)(const HostParams& hp, const gsm_step_io& io, int n_steps,
