@@ -34,7 +34,8 @@ if ROOT not in sys.path:
 
 N_AGENTS = 3
 ENVS_PER_GPU = 16384
-ROLLOUT_T = 25
+ROLLOUT_T = 25      # steps fused per launch (rollout-buffer slots)
+EPISODE_LEN = 25    # envs are re-drawn in-kernel every EPISODE_LEN steps
 SPEC_STATUS = ("declared model (SPEC.md) with UNVERIFIED constants; GS-MARL env sources withheld, "
                "parity with the reference unpinned")
 METRIC = "agent-steps/sec (graph obs+reward+cost)"
@@ -277,7 +278,7 @@ def run_gpu(args):
 
     K, W, T = args.steps, args.warmup, ROLLOUT_T
     spec_p = os.environ.get("GSM_SPEC_P", "4 (default)")
-    cfg = scenarios.load("navigation").make_world(N_AGENTS, dtype="f32", episode_length=T)
+    cfg = scenarios.load("navigation").make_world(N_AGENTS, dtype="f32", episode_length=EPISODE_LEN)
     env = MultiAgentGraphConstrainEnv(cfg, args.envs, device=local, env_offset=rank * args.envs, seed=1)
     env.reset()
     gen = torch.Generator(device=dev); gen.manual_seed(rank)
@@ -286,17 +287,14 @@ def run_gpu(args):
     ring_bytes = sum(v.numel() * v.element_size() for v in ring.values())
 
     def run_steps(n):
+        """n env steps: fused rollouts of T steps; envs finish an episode every T steps and are
+        re-drawn inside the kernel (gsm_set_auto_reset), so there is no other launch."""
         done = 0
-        while done + T <= n:
-            env.reset()                      # new episode every T steps (episode_length == T)
-            env.rollout(acts, out=ring)
-            done += T
-        if done < n:
-            env.reset()
-            for s in range(n - done):
-                io_bufs = {k: v[s] for k, v in ring.items()}
-                io = env._make_io(io_bufs, acts[s])
-                env._check(env.lib.gsm_step(env._h, __import__("ctypes").byref(io), env._stream()))
+        while done < n:
+            m = min(T, n - done)
+            env.rollout(acts[:m], out={k: v[:m] for k, v in ring.items()} if m < T else ring,
+                        auto_reset=True)
+            done += m
 
     sampler = ClockSampler(local); sampler.start()
     run_steps(max(W, 3))
@@ -312,18 +310,18 @@ def run_gpu(args):
     wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
     launches = env.kernel_launches - l0
-    n_resets = (K + T - 1) // T
+    n_resets = K // EPISODE_LEN
     clocks = sampler.stop(wall0, wall1)
 
-    # dominant kernel alone: K env-kernel launches, no resets, CUDA events on the same stream
+    # dominant kernel alone (plain variant, no auto-reset code): CUDA events on the same stream
     env.reset()
-    env.rollout(acts, out=ring)
+    env.rollout(acts, out=ring, auto_reset=False)
     torch.cuda.synchronize()
     reps = max(2, min(40, K // T))
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
     for _ in range(reps):
-        env.rollout(acts, out=ring)
+        env.rollout(acts, out=ring, auto_reset=False)
     k1.record()
     torch.cuda.synchronize()
     kern_ms = k0.elapsed_time(k1) / (reps * T)
@@ -354,6 +352,13 @@ def run_gpu(args):
         big.close()
         del bring, bacts
 
+    # ---- closed loop: a random-init graph policy (plain PyTorch, library kernels) picks the actions
+    # from obs + neighbour rows every step; one gsm_step launch per env step (BASELINE configs[4]
+    # flavour: the env feeding a policy on the same GPU, nothing leaves the device)
+    closed = None
+    if args.closed_loop_steps > 0:
+        closed = closed_loop(env, cfg, args.closed_loop_steps, dev)
+
     # ---- e2e through the numpy-facing drop-in ------------------------------------------------
     vec = GraphVecEnv(cfg, args.envs, device=local, env_offset=rank * args.envs, seed=1)
     vec.reset()
@@ -366,7 +371,7 @@ def run_gpu(args):
     t0 = time.perf_counter()
     for s in range(Ke):
         obs, graph, rew, cost, done, infos = vec.step(host_acts[s % 8])
-        if s % T == T - 1:
+        if s % EPISODE_LEN == EPISODE_LEN - 1:
             vec.reset()
     e2e_s = time.perf_counter() - t0
     stats.add(args.envs * Ke, N_AGENTS, float(rew.sum()), float(cost.sum()), float(done.sum()))
@@ -398,8 +403,9 @@ def run_gpu(args):
                 "envs_per_gpu": args.envs, "global_envs": args.envs * world,
                 "l2_policy": f"outputs rotate through a {T}-slot rollout buffer of {ring_bytes / 1e6:.0f} MB "
                              "(> 126 MB L2); no explicit flush",
-                "episode": f"reset every {T} steps ({n_resets} resets inside the timed region)",
-                "launch": f"{T} steps per CUDA-graph launch (gsm_rollout)"}),
+                "episode": f"episode_length {EPISODE_LEN}: every env is re-drawn in-kernel {n_resets} times inside the "
+                           "timed region (gsm_set_auto_reset)",
+                "launch": f"{T} fused steps per kernel launch (gsm_rollout)"}),
             "env_steps_per_s": value / N_AGENTS,
             "clocks": clocks,
             "e2e": {"value": args.envs * N_AGENTS * Ke * world / (e2e_ms * 1e-3), "unit": UNIT,
@@ -434,11 +440,55 @@ def run_gpu(args):
             line["cpu_baseline_c_port"] = cpu_c_oracle_rate()
         if world == 1 and args.large_envs > 0:
             line["roofline_large_batch"] = large
+        if closed is not None:
+            closed["value"] *= world           # every rank runs the same closed loop on its shard
+            line["closed_loop"] = closed
 
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def closed_loop(env, cfg, n_steps, dev):
+    """agent-steps/s with a random-init GS-MARL-style policy in the loop (not part of the hot
+    path: SURVEY.md §8 f3 'next' row; here only as the consumer of the env outputs)."""
+    import torch
+    torch.manual_seed(0)
+    H, K, n_act = 64, cfg.max_nbrs, len(cfg.discrete_u)
+    ego = torch.nn.Sequential(torch.nn.Linear(6, H), torch.nn.ReLU()).to(dev)
+    nbr = torch.nn.Sequential(torch.nn.Linear(6, H), torch.nn.ReLU()).to(dev)
+    att = torch.nn.Linear(H, 1).to(dev)
+    head = torch.nn.Linear(2 * H, n_act).to(dev)
+    ar = torch.arange(K, device=dev)
+
+    @torch.no_grad()
+    def act(obs, graph):
+        h = ego(obs)                                              # [B, N, H]
+        m = nbr(graph["nbr_feat"])                                # [B, N, K, H]
+        valid = ar[None, None, :] < graph["nbr_cnt"][..., None]   # padded rows masked out
+        w = att(m).squeeze(-1).masked_fill(~valid, -1e9).softmax(-1)
+        agg = (w[..., None] * m).sum(2) * valid.any(-1, keepdim=True)
+        logits = head(torch.cat([h, agg], -1))
+        g = -torch.log(-torch.log(torch.rand_like(logits).clamp_min(1e-9)))
+        return (logits + g).argmax(-1).to(torch.int32)            # Gumbel-max sample
+
+    obs, graph = env.reset()
+    for _ in range(10):
+        obs, graph, *_ = env.step(act(obs, graph))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(n_steps):
+        obs, graph, rew, cost, done, infos = env.step(act(obs, graph))
+        if (s + 1) % EPISODE_LEN == 0:
+            obs, graph = env.reset()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"value": env.n_envs * cfg.n_agents * n_steps / (ms * 1e-3), "unit": UNIT, "steps": n_steps,
+            "ms_per_step": ms / n_steps,
+            "policy": f"random-init graph-attention policy, hidden {H}, plain PyTorch eager (library kernels)"}
 
 
 def main():
@@ -451,6 +501,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--closed-loop-steps", type=int, default=200)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--ref-budget", type=float, default=90.0)
     ap.add_argument("--no-cpu", action="store_true")

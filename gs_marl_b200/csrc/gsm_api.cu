@@ -74,6 +74,7 @@ struct gsm_env {
   gsm_step_io graph_io;
   int64_t launches = 0;
   uint64_t seed = 0;
+  int auto_reset = 0;      // gsm_set_auto_reset: applies inside gsm_rollout only
   std::string err;
 };
 
@@ -424,14 +425,29 @@ int gsm_observe(gsm_env* h, const gsm_step_io* io, void* stream) {
   return do_observe(h, *io, nullptr, 0, (cudaStream_t)stream);
 }
 
+int gsm_set_auto_reset(gsm_env* h, int enabled) {
+  if (!h) return GSM_ERR_INVALID_ARG;
+  if ((enabled != 0) != (h->auto_reset != 0) && h->graph_exec) {   // cached graph has the other behaviour
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+  }
+  h->auto_reset = enabled != 0;
+  return GSM_OK;
+}
+
 int gsm_rollout(gsm_env* h, int32_t n_steps, const gsm_step_io* io, void* stream) {
   if (!h || !io || n_steps < 1) return GSM_ERR_INVALID_ARG;
   if (!io->actions) return fail(h, GSM_ERR_INVALID_ARG, "io.actions is NULL");
   DeviceGuard guard(h->device);
-  if (h->plan.spec || h->plan.big || h->plan.lane) {   // fused: all n_steps in one launch, state stays on chip
+  // fused: all n_steps in one launch, state stays on chip; the specialised and the lane kernel
+  // also re-draw finished envs in the kernel (auto-reset)
+  if (h->plan.spec || h->plan.lane || (h->plan.big && !h->auto_reset)) {
+    h->hp.auto_reset = h->auto_reset; h->hp.seed = h->seed;
     const int r = do_steps(h, *io, n_steps, (cudaStream_t)stream);
+    h->hp.auto_reset = 0;
     if (r != -1000) return r;
   }
+  if (h->auto_reset && !io->done) return fail(h, GSM_ERR_INVALID_ARG, "auto-reset rollout needs io.done");
   const bool hit = h->graph_exec && h->graph_steps == n_steps &&
                    std::memcmp(&h->graph_io, io, sizeof(gsm_step_io)) == 0;
   if (!hit) {
@@ -446,6 +462,11 @@ int gsm_rollout(gsm_env* h, int32_t n_steps, const gsm_step_io* io, void* stream
         io_set(cur, k, b ? b + (size_t)s * h->io_bytes[k] : nullptr);
       }
       st = do_step(h, cur, h->stream);
+      if (st == 0 && h->auto_reset) {                  // masked re-draw of the envs that just finished
+        const int e = is_f32(h) ? gsm::launch_reset_f32(h->hp, h->seed, cur.done, h->hp.N, h->stream)
+                                : gsm::launch_reset_f64(h->hp, h->seed, cur.done, h->hp.N, h->stream);
+        if (e) st = cuda_fail(h, e, "reset kernel launch");
+      }
     }
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
@@ -459,7 +480,7 @@ int gsm_rollout(gsm_env* h, int32_t n_steps, const gsm_step_io* io, void* stream
     h->graph_io = *io;
   }
   GSM_CUDA(h, cudaGraphLaunch(h->graph_exec, (cudaStream_t)stream));
-  h->launches += n_steps;
+  h->launches += (int64_t)n_steps * (h->auto_reset ? 3 : 1);
   return GSM_OK;
 }
 

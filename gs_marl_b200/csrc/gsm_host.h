@@ -20,6 +20,8 @@ struct HostParams {
   const void* size; const uint8_t* eflag; const void* mass; const void* accel;
   const void* max_speed; const void* slot_table;
   void* agent_state; void* lm_pos; int32_t* t; int32_t* episode;
+  int auto_reset;        // set per launch by the API layer (only gsm_rollout turns it on)
+  uint64_t seed;         // seed of the handle's last reset
 };
 
 struct RolloutStrides {  // bytes between consecutive steps of each rollout buffer

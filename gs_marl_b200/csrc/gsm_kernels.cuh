@@ -46,6 +46,11 @@ struct KParams {
   int32_t* t;              // [n_envs]
   const uint8_t* mask;     // observe-after-reset: only envs with mask[i*stride] != 0
   int64_t mask_stride;
+  // in-kernel auto-reset of fused rollouts (SPEC §8 draws, same counters as reset_kernel)
+  int auto_reset;
+  uint64_t seed;
+  int32_t* episode;        // [n_envs]
+  double ext[4];           // spawn half-extent per entity type
   const void* actions;
   T* obs; int32_t* nbr_idx; T* nbr_feat; int32_t* nbr_cnt; uint32_t* adj;
   T* reward; T* cost; uint8_t* done; int32_t* assign;
@@ -120,6 +125,28 @@ template <typename T> __device__ __forceinline__ T r_inf();
 template <> __device__ __forceinline__ float r_inf<float>() { return __int_as_float(0x7f800000); }
 template <> __device__ __forceinline__ double r_inf<double>() {
   return __longlong_as_double(0x7ff0000000000000ll);
+}
+
+// SPEC §8 draw of entity e of global env g in episode ep: the same integer stream and the same
+// fp64 arithmetic as reset_kernel / the oracle, so an in-kernel reset is bit-identical.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]);
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo);
+// Cold path (once per episode end): kept out of line so that the 10 unrolled Philox rounds do
+// not raise the register count of the step loops.
+static __device__ __noinline__ void spawn_draw_f64(uint64_t g, int ep, int e, uint64_t seed, double ext,
+                                            double* x, double* y) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)ep, (uint32_t)e, (uint32_t)seed,
+                (uint32_t)(seed >> 32), r);
+  *x = __dadd_rn(-ext, __dmul_rn(2.0 * ext, u53(r[0], r[1])));
+  *y = __dadd_rn(-ext, __dmul_rn(2.0 * ext, u53(r[2], r[3])));
+}
+template <typename T>
+__device__ __forceinline__ void spawn_draw(uint64_t g, int ep, int e, uint64_t seed, double ext, T& x, T& y) {
+  double dx, dy;
+  spawn_draw_f64(g, ep, e, seed, ext, &dx, &dy);
+  x = (T)dx; y = (T)dy;
 }
 
 // Production precision may drop contact terms that cannot change an fp32 result: for

@@ -50,8 +50,12 @@ template <typename T> __device__ __forceinline__ void st_zero16(void* p) {
   *reinterpret_cast<int4*>(p) = make_int4(0, 0, 0, 0);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(128)
+// fp32: at most 72 registers (7 CTAs of 4 warps per SM), the allocation the step loops need;
+// the cold auto-reset path must not inflate it.
+// AUTO: compiled-in auto-reset (fused rollouts with gsm_set_auto_reset); the plain variant
+// carries none of that code.
+template <typename T, bool AUTO>
+__global__ void __launch_bounds__(128, sizeof(T) == 4 ? 7 : 1)
 env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
                 const __grid_constant__ StepStrides ss) {
   extern __shared__ __align__(128) unsigned char sm[];
@@ -122,8 +126,12 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   const T size_i = ent[ii].size;
   const bool coll_i = ent[ii].flag & 1;
   const T mass_i = p.mass[ii], accel_i = p.accel[ii], maxsp_i = p.max_speed[ii];
-  const T gxl = ent[N + ii].x, gyl = ent[N + ii].y;    // own goal (static)
   int t_now = p.t[env];
+  const bool auto_reset = AUTO && p.auto_reset != 0;   // fused rollouts only (SPEC §8 draws)
+  int ep = auto_reset ? p.episode[env] : 0;
+  const int ep0 = ep;
+  const uint64_t genv = (uint64_t)(p.env_offset + env);
+  T gxl = ent[N + ii].x, gyl = ent[N + ii].y;          // own goal (static within an episode)
   const T Rs2 = p.Rs * p.Rs * (T)1.000001;             // pre-checks a few ulp inclusive
   const T cut = (T)kFarCut * p.km;
   const int64_t row = env * N + ii;
@@ -305,6 +313,23 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       }
       if (multi) __syncthreads(); else __syncwarp();
     }
+    // ---- episode end inside a fused rollout: re-draw the env's table (terminal outputs stay) ------
+    if (auto_reset) {
+      const bool rs = active && t_now >= p.episode_length;
+      if (multi) __syncthreads(); else __syncwarp();   // everyone is done reading the table
+      if (rs) {
+        spawn_draw<T>(genv, ep, i, p.seed, p.ext[GSM_ENT_AGENT], px, py);
+        vx = 0; vy = 0;
+        ent[i].x = px; ent[i].y = py; vel[2 * i] = 0; vel[2 * i + 1] = 0;
+        for (int l = i; l < L; l += N) {
+          T x, y;
+          spawn_draw<T>(genv, ep, N + l, p.seed, p.ext[ent[N + l].flag >> 1], x, y);
+          ent[N + l].x = x; ent[N + l].y = y;
+        }
+      }
+      if (multi) __syncthreads(); else __syncwarp();
+      if (rs) { gxl = ent[N + i].x; gyl = ent[N + i].y; t_now = 0; ep += 1; }
+    }
     c_act += ss.actions; c_idx += ss.nbr_idx; c_feat += ss.nbr_feat; c_obs += ss.obs;
     c_cnt += ss.nbr_cnt; c_adj += ss.adj; c_rew += ss.reward; c_cost += ss.cost;
     c_done += ss.done; c_asg += ss.assign;
@@ -315,6 +340,13 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     T* a = p.agent_state + row * 4;
     st2<T>(a, px, py); st2<T>(a + 2, vx, vy);
     if (i == 0) p.t[env] = t_now;
+    if (auto_reset && ep != ep0) {
+      for (int l = i; l < L; l += N) {
+        T* lp = p.lm_pos + (env * L + l) * 2;
+        lp[0] = ent[N + l].x; lp[1] = ent[N + l].y;
+      }
+      if (i == 0) p.episode[env] = ep;
+    }
   }
 }
 

@@ -67,7 +67,10 @@ template <typename T, int N, int P> struct SpecMinBlocks {
   static constexpr int value = (sizeof(T) == 4 && N == 3 && (P == 4 || P == 8)) ? 7 : 1;
 };
 
-template <typename T, int SCN, int N, int L, int P, bool OBS>
+// MODE 0: step(s).  MODE 1 (OBS): observe only.  MODE 2: steps with compiled-in auto-reset
+// (fused rollouts after gsm_set_auto_reset) — kept out of MODE 0 so the common loop carries
+// none of it.
+template <typename T, int SCN, int N, int L, int P, int MODE>
 __global__ void __launch_bounds__(kSpecThreads, SpecMinBlocks<T, N, P>::value)
 env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
                  const __grid_constant__ StepStrides ss) {
@@ -75,6 +78,7 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   constexpr int CH = (M + P - 1) / P;              // chunks of "others" per lane
   constexpr int W = (E + 31) / 32;
   constexpr bool LSA = SCN != GSM_SCN_NAVIGATION;
+  constexpr bool OBS = MODE == 1;
   constexpr unsigned FULL = 0xffffffffu;
   static_assert(LPE <= 32 && EPW >= 1, "an env must fit in one warp");
   static_assert(E <= 64, "adjacency is assembled in one 64-bit register");
@@ -156,6 +160,11 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     }
   }
   int t_now = p.t[env];
+  // in-kernel auto-reset (fused rollouts only): SPEC §8 draws with the counters gsm_reset uses
+  const bool auto_reset = MODE == 2 && p.auto_reset != 0;
+  int ep = auto_reset ? p.episode[env] : 0;
+  const int ep0 = ep;
+  const uint64_t genv = (uint64_t)(p.env_offset + env);
 
   // ---- per-lane output cursors (advanced by the slot strides every step) -----------------------
   const int64_t row = env * N + i;
@@ -397,6 +406,30 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         *(int32_t*)c_asg = asg;
       }
     }
+    // ---- episode end inside a fused rollout: re-draw this env (terminal outputs stay in slot s) ----
+    if (auto_reset && t_now >= p.episode_length) {
+      spawn_draw<T>(genv, ep, i, p.seed, p.ext[GSM_ENT_AGENT], px, py);
+      vx = 0; vy = 0;
+#pragma unroll
+      for (int c = 0; c < CH; c++)
+        if (e_c[c] >= N) spawn_draw<T>(genv, ep, e_c[c], p.seed, p.ext[(int)type_c[c]], lmx[c], lmy[c]);
+      if (!LSA) spawn_draw<T>(genv, ep, N + i, p.seed, p.ext[p.eflag[N + i] >> 1], goalx, goaly);
+      if (LSA && off < N) {
+        T ax, ay, bx = 0, by = 0;
+        spawn_draw<T>(genv, ep, N, p.seed, p.ext[p.eflag[N] >> 1], ax, ay);
+        if (L > 1) spawn_draw<T>(genv, ep, N + 1, p.seed, p.ext[p.eflag[N + 1] >> 1], bx, by);
+        if (SCN == GSM_SCN_POLYGON) {
+          slotx = ax + p.poly_r * p.slot_table[2 * off];
+          sloty = ay + p.poly_r * p.slot_table[2 * off + 1];
+        } else {
+          const T f = p.slot_table[2 * off];
+          slotx = ax + f * (bx - ax);
+          sloty = ay + f * (by - ay);
+        }
+      }
+      t_now = 0;
+      ep += 1;
+    }
     // advance the cursors to the next slot of the rollout buffers
     c_idx += ss.nbr_idx; c_feat += ss.nbr_feat; c_obs += ss.obs;
     if (ROLES) c_role += role_stride;
@@ -411,6 +444,15 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     T* a = p.agent_state + row * 4;
     st2<T>(a, px, py); st2<T>(a + 2, vx, vy);
     if (i == 0) p.t[env] = t_now;
+  }
+  if (auto_reset && ep != ep0 && active) {             // the landmarks of the last re-draw + episode count
+    for (int l = off; l < L; l += LPE) {
+      T x, y;
+      spawn_draw<T>(genv, ep - 1, N + l, p.seed, p.ext[p.eflag[N + l] >> 1], x, y);
+      T* lp = p.lm_pos + (env * L + l) * 2;
+      lp[0] = x; lp[1] = y;
+    }
+    if (off == 0) p.episode[env] = ep;
   }
 }
 

@@ -91,6 +91,8 @@ static void fill_kparams(KParams<GSM_REAL>& kp, const HostParams& hp, const gsm_
   kp.slot_table = (const T*)hp.slot_table;
   kp.agent_state = (T*)hp.agent_state; kp.lm_pos = (T*)hp.lm_pos; kp.t = hp.t;
   kp.mask = mask; kp.mask_stride = mask_stride;
+  kp.auto_reset = hp.auto_reset; kp.seed = hp.seed; kp.episode = hp.episode;
+  for (int k = 0; k < 4; k++) kp.ext[k] = hp.ext[k];
   kp.actions = io.actions;
   kp.obs = (T*)io.obs; kp.nbr_idx = io.nbr_idx; kp.nbr_feat = (T*)io.nbr_feat;
   kp.nbr_cnt = io.nbr_cnt; kp.adj = io.adj; kp.reward = (T*)io.reward; kp.cost = (T*)io.cost;
@@ -167,9 +169,11 @@ static int launch_spec_one(const KParams<GSM_REAL>& kp, int n_steps, const StepS
   const int64_t grid = (kp.n_envs + EPW * WPC - 1) / (EPW * WPC);
   const size_t smem = SCN == GSM_SCN_NAVIGATION ? 0 : (size_t)WPC * EPW * N * N * sizeof(GSM_REAL);
   if (observe)
-    env_steps_kernel<GSM_REAL, SCN, N, L, P, true><<<(unsigned)grid, kSpecThreads, smem, st>>>(kp, 1, ss);
+    env_steps_kernel<GSM_REAL, SCN, N, L, P, 1><<<(unsigned)grid, kSpecThreads, smem, st>>>(kp, 1, ss);
+  else if (kp.auto_reset)
+    env_steps_kernel<GSM_REAL, SCN, N, L, P, 2><<<(unsigned)grid, kSpecThreads, smem, st>>>(kp, n_steps, ss);
   else
-    env_steps_kernel<GSM_REAL, SCN, N, L, P, false><<<(unsigned)grid, kSpecThreads, smem, st>>>(kp, n_steps, ss);
+    env_steps_kernel<GSM_REAL, SCN, N, L, P, 0><<<(unsigned)grid, kSpecThreads, smem, st>>>(kp, n_steps, ss);
   return (int)cudaGetLastError();
 }
 
@@ -245,7 +249,7 @@ int GSM_SFX(launch_lane)(const HostParams& hp, const gsm_step_io& io, int n_step
   const LaneGeom g = lane_geom(hp.N);
   const size_t smem = lane_smem((int)sizeof(LaneEnt<GSM_REAL>), (int)sizeof(GSM_REAL), hp.N, hp.N + hp.L,
                                 g.envs_per_cta);
-  auto k = env_lane_kernel<GSM_REAL>;
+  auto k = hp.auto_reset ? env_lane_kernel<GSM_REAL, true> : env_lane_kernel<GSM_REAL, false>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

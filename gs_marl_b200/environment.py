@@ -140,9 +140,11 @@ class MultiAgentGraphConstrainEnv:
                                                self.world.n_agents, C.byref(self._io), self._stream()))
         return self._result(self.buf)
 
-    def rollout(self, actions, out: Optional[dict] = None) -> dict:
-        """T steps from one CUDA-graph launch; actions [T, n_envs, N(,2)]; returns dict of
-        [T, ...] tensors (the rollout-buffer layout)."""
+    def rollout(self, actions, out: Optional[dict] = None, auto_reset: Optional[bool] = None) -> dict:
+        """T steps in one launch (fused kernel, or a CUDA graph for shapes without one); actions
+        [T, n_envs, N(,2)]; returns dict of [T, ...] tensors (the rollout-buffer layout,
+        SURVEY.md §8 f2).  auto_reset (default: the env's flag): envs that finish inside the
+        rollout keep their terminal outputs in that slot and are re-drawn before the next step."""
         dt, shape = self._shapes["actions"]
         a = torch.as_tensor(actions, device=self.device).to(_TORCH_DT[dt]).contiguous()
         T = a.shape[0]
@@ -151,7 +153,9 @@ class MultiAgentGraphConstrainEnv:
         if out is None:
             out = {k: self._alloc(k, (T,)) for k in self.OUTPUTS}
         io = self._make_io(out, a)
+        ar = self.auto_reset if auto_reset is None else bool(auto_reset)
         with torch.cuda.device(self.device):
+            self._check(self.lib.gsm_set_auto_reset(self._h, int(ar)))
             self._check(self.lib.gsm_rollout(self._h, T, C.byref(io), self._stream()))
         out["actions"] = a
         return out

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GSM_ABI_VERSION 3
+#define GSM_ABI_VERSION 4
 
 #define GSM_OBS_DIM 6        /* vx, vy, px, py, target_dx, target_dy          (SPEC.md §6) */
 #define GSM_NBR_FEAT_DIM 6   /* dx, dy, dvx, dvy, dist, (real)entity_type     (SPEC.md §6) */
@@ -177,6 +177,12 @@ int gsm_step(gsm_env* h, const gsm_step_io* io, void* stream);
  * + s*<that buffer's gsm_io_sizes entry> (i.e. io points at slot 0 of [T][...]
  * rollout-buffer tensors). */
 int gsm_rollout(gsm_env* h, int32_t n_steps, const gsm_step_io* io, void* stream);
+
+/* Auto-reset inside gsm_rollout (the vec-env wrapper's "reset when done", env_wrappers.py
+ * SOURCES.txt:11): when enabled, an env whose step counter reaches episode_length at step s
+ * keeps its terminal outputs in slot s and is re-drawn (same Philox stream as gsm_reset with
+ * the handle's current seed) before step s+1.  gsm_step is not affected. */
+int gsm_set_auto_reset(gsm_env* h, int enabled);
 
 /* _get_obs + graph build for the current state, no physics (environment.py). */
 int gsm_observe(gsm_env* h, const gsm_step_io* io, void* stream);

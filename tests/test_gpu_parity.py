@@ -457,3 +457,47 @@ def test_host_path_with_caller_owned_buffers_and_lsa_zero_problems():
     assert lib.gsm_destroy(h) == 0
     assert lib.gsm_lsa(bufs["obs"].ctypes.data, bufs["assign"].ctypes.data, 0, 4, abi.GSM_F64, 0, None) == 0
     assert lib.gsm_lsa(None, None, 1, 4, abi.GSM_F64, 0, None) == -1
+
+
+@pytest.mark.parametrize("name,N,kw,env_vars", [
+    ("navigation", 3, {}, {}),                                   # specialised kernel, in-kernel re-draw
+    ("polygon", 6, {}, {}),                                      # specialised + LSA slots re-derived
+    ("line", 4, {}, {}),
+    ("navigation", 12, {}, {}),                                  # lane kernel, 2 envs per warp
+    ("navigation", 40, {"max_nbrs": 16}, {}),                    # lane kernel, env spans 2 warps
+    ("navigation", 24, {"max_nbrs": 16}, {"GSM_NO_LANE": "1"}),  # CTA-per-env kernel -> graph fallback
+    ("navigation", 33, {"n_obstacles": 0, "max_nbrs": 65}, {"GSM_NO_LANE": "1"}),   # generic -> graph fallback
+])
+def test_rollout_auto_reset_matches_oracle_resets(name, N, kw, env_vars, monkeypatch):
+    """gsm_set_auto_reset + gsm_rollout: envs that finish inside the rollout keep their terminal
+    outputs and restart from the SPEC §8 draw — bit-identical to resetting the oracle by hand,
+    including envs that finish on different steps."""
+    from oracle import gsm_oracle as O
+    for k, v in env_vars.items():
+        monkeypatch.setenv(k, v)
+    cfg = make_cfg(name, N, "f64", episode_length=4, **kw)
+    B, T, seed = 13, 11, 99
+    o = O.OracleEnv(cfg, B)
+    o.reset(seed)
+    o.step_count[:] = np.arange(B) % 4                     # staggered episode ends
+    env = _env(cfg, B, seed=seed)
+    env.reset()
+    env.set_state(None, None, o.step_count)
+    acts = random_actions(cfg, np.random.default_rng(1), (T, B))
+    wants = []
+    for t in range(T):
+        w = {k: v.copy() for k, v in o.step(acts[t]).items()}
+        wants.append(w)
+        if w["done"].any():
+            o.reset(seed, w["done"][:, 0].copy())
+    roll = _np(env.rollout(acts, auto_reset=True))
+    for t in range(T):
+        assert_match({k: roll[k][t] for k in OUT_KEYS}, wants[t], rtol=F64_RTOL, atol=F64_ATOL,
+                     ctx=f"{name}{N} auto-reset t={t}")
+    ag, lm, tt = env.get_state()
+    np.testing.assert_allclose(ag.cpu().numpy(), o.agent_state, rtol=F64_RTOL, atol=F64_ATOL)
+    assert (lm.cpu().numpy() == o.landmark_pos).all() and (tt.cpu().numpy() == o.step_count).all()
+    o.reset(seed)                                          # the episode counters advanced identically
+    env.reset()
+    assert (env.get_state()[0].cpu().numpy() == o.agent_state).all()
+    env.close()
