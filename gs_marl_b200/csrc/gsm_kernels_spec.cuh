@@ -408,11 +408,16 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     }
     // ---- episode end inside a fused rollout: re-draw this env (terminal outputs stay in slot s) ----
     if (auto_reset && t_now >= p.episode_length) {
+      // cold path: everything is recomputed from (i, sub, off) and global memory here, so the
+      // per-chunk constants of the hot loop do not have to stay live for it
       spawn_draw<T>(genv, ep, i, p.seed, p.ext[GSM_ENT_AGENT], px, py);
       vx = 0; vy = 0;
 #pragma unroll
-      for (int c = 0; c < CH; c++)
-        if (e_c[c] >= N) spawn_draw<T>(genv, ep, e_c[c], p.seed, p.ext[(int)type_c[c]], lmx[c], lmy[c]);
+      for (int c = 0; c < CH; c++) {
+        const int o = c * P + sub;
+        const int e = o + (o >= i ? 1 : 0);
+        if (o < M && e >= N) spawn_draw<T>(genv, ep, e, p.seed, p.ext[p.eflag[e] >> 1], lmx[c], lmy[c]);
+      }
       if (!LSA) spawn_draw<T>(genv, ep, N + i, p.seed, p.ext[p.eflag[N + i] >> 1], goalx, goaly);
       if (LSA && off < N) {
         T ax, ay, bx = 0, by = 0;
