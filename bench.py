@@ -198,7 +198,8 @@ def cpu_rate(total_budget_s, n_steps):
         probe.step()
     per_env_step = (time.perf_counter() - t0) / 3 / 2          # seconds per env-step per core
     probe.close()
-    envs = int(max(cores, min(ENVS_PER_GPU, total_budget_s / max(n_steps, 1) / per_env_step * cores)))
+    # at least 8 envs per worker so that pipe round-trips do not dominate what is measured
+    envs = int(max(cores * 8, min(ENVS_PER_GPU, total_budget_s / max(n_steps, 1) / per_env_step * cores)))
     return cores, envs
 
 
