@@ -190,7 +190,10 @@ int do_steps(gsm_env* h, const gsm_step_io& io, int n_steps, cudaStream_t st, in
     rs.done = (int64_t)h->io_bytes[IO_DONE]; rs.assign = (int64_t)h->io_bytes[IO_ASSIGN];
   }
   int e = -1;
-  if (h->plan.spec)
+  if (h->plan.team && !observe)
+    e = is_f32(h) ? gsm::launch_team_f32(h->hp, io, n_steps, rs, st)
+                  : gsm::launch_team_f64(h->hp, io, n_steps, rs, st);
+  else if (h->plan.spec)
     e = is_f32(h) ? gsm::launch_spec_f32(h->hp, io, n_steps, rs, observe, mask, mask_stride, st)
                   : gsm::launch_spec_f64(h->hp, io, n_steps, rs, observe, mask, mask_stride, st);
   else if (h->plan.lane && !observe)

@@ -38,6 +38,7 @@ struct LaunchPlan {     // chosen once per handle
   int spec;             // 1: a size-specialised register-resident kernel exists (gsm_kernels_spec.cuh)
   int big;              // 1: the large-team CTA-per-env kernel applies (gsm_kernels_big.cuh)
   int lane;             // 1: the lane-per-agent kernel applies (gsm_kernels_lane.cuh)
+  int team;             // 1: a polygon/line group-LSA instance exists (gsm_kernels_team.cuh)
 };
 
 // Each returns a cudaError_t (as int).  physics: 1 = full step, 0 = observe only.
@@ -65,6 +66,11 @@ int launch_big_f64(const HostParams& hp, const gsm_step_io& io, int n_steps,
 int launch_lane_f32(const HostParams& hp, const gsm_step_io& io, int n_steps,
                     const RolloutStrides& rs, cudaStream_t st);
 int launch_lane_f64(const HostParams& hp, const gsm_step_io& io, int n_steps,
+                    const RolloutStrides& rs, cudaStream_t st);
+// Polygon / line kernel with the group-parallel assignment; returns -1 if no instance.
+int launch_team_f32(const HostParams& hp, const gsm_step_io& io, int n_steps,
+                    const RolloutStrides& rs, cudaStream_t st);
+int launch_team_f64(const HostParams& hp, const gsm_step_io& io, int n_steps,
                     const RolloutStrides& rs, cudaStream_t st);
 int launch_reset_f32(const HostParams& hp, uint64_t seed, const uint8_t* mask, int64_t mask_stride,
                      cudaStream_t st);

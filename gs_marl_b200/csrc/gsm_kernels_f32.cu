@@ -1,6 +1,7 @@
 // Production precision (fp32).  FMA contraction allowed.
 #include "gsm_kernels_big.cuh"
 #include "gsm_kernels_lane.cuh"
+#include "gsm_kernels_team.cuh"
 #define GSM_REAL float
 #define GSM_SFX(name) name##_f32
 #include "gsm_launch.inl"

@@ -2,6 +2,7 @@
 // rounds once, in the order SPEC.md writes it, like the CPU oracle.
 #include "gsm_kernels_big.cuh"
 #include "gsm_kernels_lane.cuh"
+#include "gsm_kernels_team.cuh"
 #define GSM_REAL double
 #define GSM_SFX(name) name##_f64
 #include "gsm_launch.inl"

@@ -1,0 +1,414 @@
+// gsm_kernels_team.cuh — polygon / line kernel with the per-step linear assignment
+// (SPEC.md §2-7; reference scenarios/simple_formation.py, simple_line.py — SOURCES.txt:24-25,
+// readme.md:89-90; scipy.optimize.linear_sum_assignment, requirements.txt:101).
+//
+// The assignment dominates these scenarios (profiles/README.md: 85 % of the instructions with
+// one lane per column and 2 problems per warp).  Here an env is served by a GROUP of G lanes
+// and every lane owns A = N / G agents, which are also its A assignment rows, A columns and A
+// slots of scipy's `remaining` order — so a warp solves 32 / G problems in lockstep (8 for
+// N = 12, 16 for N = 6, 32 for N <= 5) and all per-lane solver state (u, v, shortest-path
+// costs, path, row4col, col4row, positions) is statically indexed registers.  Group-wide
+// minimum / tie-rule maximum are log2(G) xor-shuffles; the tie rule of scipy's scan ("last
+// unassigned minimum in `remaining` order, else the first") is one max over packed keys.
+// Physics and the neighbour graph use the same layout (a lane sweeps the other agents for
+// each of its A agents from a shared-memory position table), rows go to HBM over a
+// warp-cooperative coalesced clear like in env_lane_kernel, and `n_steps` steps are fused.
+#pragma once
+#include "gsm_kernels_spec.cuh"
+
+namespace gsm {
+
+template <typename T, int A>
+__device__ __forceinline__ T sel(const T (&arr)[A], int idx) {
+  T r = arr[0];
+#pragma unroll
+  for (int a = 1; a < A; a++) r = idx == a ? arr[a] : r;
+  return r;
+}
+
+// scipy rectangular_lsap on N x N costs in shared memory, G lanes per problem, A = N / G rows
+// and columns per lane (row / column j belongs to lane j / A of the group, local index j % A).
+// Every lane of the warp calls it; groups are aligned runs of G lanes starting at `base`.
+// Returns col4row of the lane's A rows in c4r[].  Loops are bounded by N (no hang on NaN).
+template <typename T, int N, int G>
+__device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int base, bool live,
+                                          int (&c4r)[N / G]) {
+  constexpr int A = N / G;
+  constexpr unsigned FULL = 0xffffffffu;
+  const T INF = r_inf<T>();
+  T u[A], v[A], spc[A];
+  int path[A], r4c[A], pos[A];
+#pragma unroll
+  for (int a = 0; a < A; a++) { u[a] = 0; v[a] = 0; path[a] = -1; r4c[a] = -1; c4r[a] = -1; spc[a] = INF; pos[a] = 0; }
+  for (int cur = 0; cur < N; cur++) {
+    T minval = 0;
+    int i = cur, nrem = N, sink = live ? -1 : 0;
+    unsigned inrem = live ? ((1u << A) - 1u) : 0u, sr = 0, sc = 0;
+#pragma unroll
+    for (int a = 0; a < A; a++) { spc[a] = INF; pos[a] = N - 1 - (g * A + a); }
+    for (int iter = 0; iter < N && __any_sync(FULL, sink == -1); iter++) {
+      const bool run = sink == -1;
+      const int ig = i / A, il = i - ig * A;
+      if (run && ig == g) sr |= 1u << il;
+      const T u_i = shfl(FULL, sel<T, A>(u, il), base + ig);
+      T lo = INF;
+#pragma unroll
+      for (int a = 0; a < A; a++) {
+        if (run && ((inrem >> a) & 1u)) {
+          const T r = minval + C[i * N + g * A + a] - u_i - v[a];
+          if (r < spc[a]) { path[a] = i; spc[a] = r; }
+        }
+        if ((inrem >> a) & 1u) lo = spc[a] < lo ? spc[a] : lo;
+      }
+#pragma unroll
+      for (int m = G / 2; m >= 1; m >>= 1) {
+        const T o = __shfl_xor_sync(FULL, lo, m);
+        lo = o < lo ? o : lo;
+      }
+      // tie rule: an unassigned minimum with the largest position wins, else the minimum with
+      // the smallest position; positions are unique, the column index rides in the low bits
+      int best = -1;
+#pragma unroll
+      for (int a = 0; a < A; a++) {
+        if (((inrem >> a) & 1u) && spc[a] == lo) {
+          const int key = r4c[a] == -1 ? 64 + pos[a] : 31 - pos[a];
+          const int packed = (key << 6) | (g * A + a);
+          best = packed > best ? packed : best;
+        }
+      }
+#pragma unroll
+      for (int m = G / 2; m >= 1; m >>= 1) {
+        const int o = __shfl_xor_sync(FULL, best, m);
+        best = o > best ? o : best;
+      }
+      const int key = best >> 6, j = best < 0 ? 0 : (best & 63);
+      const int selpos = key >= 64 ? key - 64 : 31 - key;
+      const int jg = j / A, jl = j - jg * A;
+      const int r4c_j = shfl(FULL, sel<int, A>(r4c, jl), base + jg);
+      if (run && best >= 0) {
+        minval = lo;
+        if (r4c_j == -1) sink = j; else i = r4c_j;
+        if (jg == g) { sc |= 1u << jl; inrem &= ~(1u << jl); }
+        nrem--;
+#pragma unroll
+        for (int a = 0; a < A; a++)
+          if (((inrem >> a) & 1u) && pos[a] == nrem) pos[a] = selpos;
+      }
+    }
+    // dual update (col4row as it was before this augmentation)
+#pragma unroll
+    for (int a = 0; a < A; a++) {
+      const int c = c4r[a] < 0 ? 0 : c4r[a];
+      const int cg = c / A, cl = c - cg * A;
+      T val = 0;
+#pragma unroll
+      for (int k = 0; k < A; k++) {
+        const T t = shfl(FULL, spc[k], base + cg);
+        if (cl == k) val = t;
+      }
+      if (live) {
+        if (g * A + a == cur) u[a] += minval;
+        else if ((sr >> a) & 1u) u[a] += minval - val;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < A; a++)
+      if ((sc >> a) & 1u) v[a] -= minval - spc[a];
+    // augment along the path
+    int j = sink < 0 ? 0 : sink;
+    bool going = live && sink >= 0;
+    for (int iter = 0; iter < N && __any_sync(FULL, going); iter++) {
+      const int jg = j / A, jl = j - jg * A;
+      int arow = shfl(FULL, sel<int, A>(path, jl), base + jg);
+      arow = arow < 0 ? 0 : arow;
+      const int ag = arow / A, al = arow - ag * A;
+      const int tprev = shfl(FULL, sel<int, A>(c4r, al), base + ag);
+      if (going) {
+#pragma unroll
+        for (int a = 0; a < A; a++) {
+          if (jg == g && jl == a) r4c[a] = arow;
+          if (ag == g && al == a) c4r[a] = j;
+        }
+        j = tprev < 0 ? 0 : tprev;
+        if (arow == cur) going = false;
+      }
+    }
+  }
+}
+
+constexpr int kTeamThreads = 128;
+
+__host__ __device__ inline size_t team_env_bytes(int rb, int N) {
+  // per env: agent positions + velocities, N x N costs, shared-reward scratch
+  return ((size_t)(4 * N + N * N + N) * rb + 15) / 16 * 16;
+}
+
+template <typename T, int SCN, int N, int G>
+__global__ void __launch_bounds__(kTeamThreads)
+env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
+                const __grid_constant__ StepStrides ss) {
+  constexpr int A = N / G, EPW = 32 / G, L = SCN == GSM_SCN_POLYGON ? 1 : 2, E = N + L;
+  static_assert(N % G == 0 && (G & (G - 1)) == 0 && G <= 32, "G lanes per env, A agents per lane");
+  static_assert(E <= 32, "adjacency is one 32-bit word");
+  typedef Arith<T> AR;
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int K = p.K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane % G, grp = lane / G, base = grp * G;
+  const int64_t env_w0 = ((int64_t)blockIdx.x * (kTeamThreads / 32) + warp) * EPW;   // first env of the warp
+  const int64_t env_raw = env_w0 + grp;
+  const bool live = env_raw < p.n_envs;
+  const int64_t env = live ? env_raw : 0;                 // shadow groups compute, never store
+
+  const size_t eb = team_env_bytes((int)sizeof(T), N);
+  T* e_sm = (T*)(sm + (size_t)(warp * EPW + grp) * eb);
+  T* apos = e_sm;                                         // [N][2]
+  T* avel = e_sm + 2 * N;                                 // [N][2]
+  T* cmat = e_sm + 4 * N;                                 // [N][N]
+  T* rsm = e_sm + 4 * N + N * N;                          // [N]
+
+  // ---- my A agents ----------------------------------------------------------------------------
+  T px[A], py[A], vx[A], vy[A], size_a[A], mass_a[A], accel_a[A], maxsp_a[A];
+  bool coll_a[A];
+#pragma unroll
+  for (int a = 0; a < A; a++) {
+    const int i = g * A + a;
+    const T* s = p.agent_state + (env * N + i) * 4;
+    px[a] = s[0]; py[a] = s[1]; vx[a] = s[2]; vy[a] = s[3];
+    size_a[a] = p.size[i]; coll_a[a] = p.eflag[i] & 1;
+    mass_a[a] = p.mass[i]; accel_a[a] = p.accel[i]; maxsp_a[a] = p.max_speed[i];
+    apos[2 * i] = px[a]; apos[2 * i + 1] = py[a]; avel[2 * i] = vx[a]; avel[2 * i + 1] = vy[a];
+  }
+  T mx[L], my[L], msize[L];
+  int mflag[L];
+#pragma unroll
+  for (int l = 0; l < L; l++) {
+    const T* m = p.lm_pos + (env * L + l) * 2;
+    mx[l] = m[0]; my[l] = m[1]; msize[l] = p.size[N + l]; mflag[l] = p.eflag[N + l];
+  }
+  int t_now = p.t[env];
+  const bool auto_reset = p.auto_reset != 0;
+  int ep = auto_reset ? p.episode[env] : 0;
+  const int ep0 = ep;
+  const uint64_t genv = (uint64_t)(p.env_offset + env);
+  const T cut = (T)kFarCut * p.km;
+  __syncwarp();
+
+  const unsigned char* c_act = (const unsigned char*)p.actions;
+  unsigned char* c_obs = (unsigned char*)p.obs;
+  unsigned char* c_idx = (unsigned char*)p.nbr_idx;
+  unsigned char* c_feat = (unsigned char*)p.nbr_feat;
+  unsigned char* c_cnt = (unsigned char*)p.nbr_cnt;
+  unsigned char* c_adj = (unsigned char*)p.adj;
+  unsigned char* c_rew = (unsigned char*)p.reward;
+  unsigned char* c_cost = (unsigned char*)p.cost;
+  unsigned char* c_done = (unsigned char*)p.done;
+  unsigned char* c_asg = (unsigned char*)p.assign;
+
+  for (int step = 0; step < n_steps; step++) {
+    // ---- SPEC §2-4 for my A agents (position table = state at the start of the step) ----------
+#pragma unroll
+    for (int a = 0; a < A; a++) {
+      const int i = g * A + a;
+      const int64_t row = env * N + i;
+      T ux = 0, uy = 0;
+      if (p.action_mode == GSM_ACT_DISCRETE) {
+        const int ac = ((const int32_t*)c_act)[row];
+        if (ac >= 0 && ac < p.n_actions) { ux = p.discrete_u[ac][0]; uy = p.discrete_u[ac][1]; }
+      } else { ux = ((const T*)c_act)[row * 2]; uy = ((const T*)c_act)[row * 2 + 1]; }
+      T fx = accel_a[a] * ux, fy = accel_a[a] * uy;
+      if (coll_a[a]) {
+        for (int j = 0; j < E; j++) {
+          if (j == i) continue;
+          T qx, qy, qs;
+          bool qc;
+          if (j < N) { qx = apos[2 * j]; qy = apos[2 * j + 1]; qs = p.size[j]; qc = p.eflag[j] & 1; }
+          else { qx = mx[j - N < L ? j - N : 0]; qy = my[j - N < L ? j - N : 0]; qs = msize[j - N < L ? j - N : 0]; qc = mflag[j - N < L ? j - N : 0] & 1; }
+          if (!qc) continue;
+          const T dx = px[a] - qx, dy = py[a] - qy;
+          const T d2 = dx * dx + dy * dy;
+          const T dmin = size_a[a] + qs;
+          if (Prec<T>::kCut) { const T far = dmin + cut; if (d2 > far * far) continue; }
+          const T dist = AR::sqrt(d2);
+          const T x = AR::div_const(-(dist - dmin), p.km, p.km_inv);
+          if (Prec<T>::kCut && x < (T)(-kFarCut)) continue;
+          const T pen = softplus(x) * p.km;
+          fx = fx + AR::div(p.cf * dx, dist) * pen;
+          fy = fy + AR::div(p.cf * dy, dist) * pen;
+        }
+      }
+      T nvx = vx[a] * p.one_minus_damp, nvy = vy[a] * p.one_minus_damp;
+      nvx = nvx + AR::div(fx, mass_a[a]) * p.dt;
+      nvy = nvy + AR::div(fy, mass_a[a]) * p.dt;
+      if (maxsp_a[a] > (T)0) {
+        const T sp = AR::sqrt(nvx * nvx + nvy * nvy);
+        if (sp > maxsp_a[a]) { nvx = AR::div(nvx, sp) * maxsp_a[a]; nvy = AR::div(nvy, sp) * maxsp_a[a]; }
+      }
+      vx[a] = nvx; vy[a] = nvy;
+      px[a] = px[a] + nvx * p.dt; py[a] = py[a] + nvy * p.dt;
+    }
+    t_now += 1;
+    __syncwarp();                                          // every lane has read the old table
+#pragma unroll
+    for (int a = 0; a < A; a++) {
+      const int i = g * A + a;
+      apos[2 * i] = px[a]; apos[2 * i + 1] = py[a]; avel[2 * i] = vx[a]; avel[2 * i + 1] = vy[a];
+    }
+    __syncwarp();
+
+    // ---- SPEC §5: slots of my A columns, cost columns, group-parallel assignment --------------
+    T sx[A], sy[A];
+#pragma unroll
+    for (int a = 0; a < A; a++) {
+      const int k = g * A + a;
+      if (SCN == GSM_SCN_POLYGON) {
+        sx[a] = mx[0] + p.poly_r * p.slot_table[2 * k];
+        sy[a] = my[0] + p.poly_r * p.slot_table[2 * k + 1];
+      } else {
+        const T f = p.slot_table[2 * k];
+        sx[a] = mx[0] + f * (mx[L - 1] - mx[0]);
+        sy[a] = my[0] + f * (my[L - 1] - my[0]);
+      }
+      for (int r = 0; r < N; r++) {
+        const T dx = sx[a] - apos[2 * r], dy = sy[a] - apos[2 * r + 1];
+        cmat[r * N + k] = r_sqrt(dx * dx + dy * dy);
+      }
+    }
+    __syncwarp();
+    int c4r[A];
+    lsa_group<T, N, G>(cmat, g, base, true, c4r);
+    __syncwarp();
+
+    // ---- padding first: the rows of this warp's envs are one contiguous region -------------------
+    {
+      int64_t ne = p.n_envs - env_w0;
+      ne = ne > EPW ? EPW : (ne < 0 ? 0 : ne);
+      const int64_t row0 = env_w0 * N, nrows = ne * N;
+      unsigned char* zi = c_idx + row0 * K * 4;
+      const int64_t bi = nrows * K * 4;
+      if ((((uintptr_t)zi | (uintptr_t)bi) & 15) == 0) {
+        for (int64_t q = (int64_t)lane * 16; q < bi; q += 512) *reinterpret_cast<int4*>(zi + q) = make_int4(-1, -1, -1, -1);
+      } else {
+        for (int64_t q = (int64_t)lane * 4; q < bi; q += 128) *reinterpret_cast<int32_t*>(zi + q) = -1;
+      }
+      unsigned char* zf = c_feat + row0 * K * GSM_NBR_FEAT_DIM * (int64_t)sizeof(T);
+      const int64_t bf = nrows * K * GSM_NBR_FEAT_DIM * (int64_t)sizeof(T);
+      if ((((uintptr_t)zf | (uintptr_t)bf) & 15) == 0) {
+        for (int64_t q = (int64_t)lane * 16; q < bf; q += 512) *reinterpret_cast<int4*>(zf + q) = make_int4(0, 0, 0, 0);
+      } else {
+        for (int64_t q = (int64_t)lane * sizeof(T); q < bf; q += 32 * sizeof(T)) *reinterpret_cast<T*>(zf + q) = (T)0;
+      }
+      __syncwarp();
+    }
+
+    // ---- SPEC §6-7 for my A agents ---------------------------------------------------------------
+    T rew[A];
+#pragma unroll
+    for (int a = 0; a < A; a++) {
+      const int i = g * A + a;
+      const int64_t row = env * N + i;
+      int cnt = 0, ncol = 0;
+      uint32_t word = 0;
+      int32_t* g_idx = (int32_t*)c_idx + row * K;
+      T* g_feat = (T*)c_feat + row * K * GSM_NBR_FEAT_DIM;
+      for (int e = 0; e < E; e++) {
+        if (e == i) continue;
+        T ex, ey, evx = 0, evy = 0, es;
+        int fl;
+        if (e < N) { ex = apos[2 * e]; ey = apos[2 * e + 1]; evx = avel[2 * e]; evy = avel[2 * e + 1]; es = p.size[e]; fl = p.eflag[e]; }
+        else { const int l = e - N < L ? e - N : 0; ex = mx[l]; ey = my[l]; es = msize[l]; fl = mflag[l]; }
+        const T dx = ex - px[a], dy = ey - py[a];
+        const T dist = AR::sqrt(dx * dx + dy * dy);
+        if (dist < size_a[a] + es && (e < N || (p.cost_obstacles && (fl >> 1) == GSM_ENT_OBSTACLE))) ncol++;
+        if (dist < p.Rs) {
+          word |= 1u << e;
+          if (cnt < K && live) {
+            g_idx[cnt] = e;
+            T* f = g_feat + cnt * GSM_NBR_FEAT_DIM;
+            st2<T>(f, dx, dy); st2<T>(f + 2, evx - vx[a], evy - vy[a]); st2<T>(f + 4, dist, (T)(fl >> 1));
+          }
+          cnt++;
+        }
+      }
+      if (cnt > K) cnt = K;
+      const int k = c4r[a] < 0 ? 0 : c4r[a];
+      T tx, ty;
+      if (SCN == GSM_SCN_POLYGON) {
+        tx = mx[0] + p.poly_r * p.slot_table[2 * k];
+        ty = my[0] + p.poly_r * p.slot_table[2 * k + 1];
+      } else {
+        const T f = p.slot_table[2 * k];
+        tx = mx[0] + f * (mx[L - 1] - mx[0]);
+        ty = my[0] + f * (my[L - 1] - my[0]);
+      }
+      const T gx = tx - px[a], gy = ty - py[a];
+      const T d = AR::sqrt(gx * gx + gy * gy);
+      rew[a] = ((T)0 - p.w_dist * d) + (d < p.goal_tol ? p.w_goal : (T)0);
+      if (live) {
+        T* o = (T*)c_obs + row * GSM_OBS_DIM;
+        st2<T>(o, vx[a], vy[a]); st2<T>(o + 2, px[a], py[a]); st2<T>(o + 4, gx, gy);
+        ((int32_t*)c_cnt)[row] = cnt;
+        ((uint32_t*)c_adj)[row] = word;
+        ((T*)c_cost)[row] = (T)ncol;
+        c_done[row] = (uint8_t)(t_now >= p.episode_length);
+        ((int32_t*)c_asg)[row] = c4r[a];
+        if (!p.share_reward) ((T*)c_rew)[row] = rew[a];
+      }
+    }
+    if (p.share_reward) {                                  // mean over the env's agents, ascending order
+#pragma unroll
+      for (int a = 0; a < A; a++) rsm[g * A + a] = rew[a];
+      __syncwarp();
+      T s = rsm[0];
+      for (int k = 1; k < N; k++) s = s + rsm[k];
+      s = s / (T)N;
+      if (live) {
+#pragma unroll
+        for (int a = 0; a < A; a++) ((T*)c_rew)[env * N + g * A + a] = s;
+      }
+      __syncwarp();
+    }
+
+    // ---- episode end inside a fused rollout (SPEC §8 draws, cold) ----------------------------------
+    if (auto_reset && t_now >= p.episode_length) {
+#pragma unroll
+      for (int a = 0; a < A; a++) {
+        spawn_draw<T>(genv, ep, g * A + a, p.seed, p.ext[GSM_ENT_AGENT], px[a], py[a]);
+        vx[a] = 0; vy[a] = 0;
+      }
+#pragma unroll
+      for (int l = 0; l < L; l++) spawn_draw<T>(genv, ep, N + l, p.seed, p.ext[mflag[l] >> 1], mx[l], my[l]);
+      t_now = 0;
+      ep += 1;
+    }
+    if (auto_reset) {                                      // the table must show the re-drawn agents
+      __syncwarp();
+#pragma unroll
+      for (int a = 0; a < A; a++) {
+        const int i = g * A + a;
+        apos[2 * i] = px[a]; apos[2 * i + 1] = py[a]; avel[2 * i] = vx[a]; avel[2 * i + 1] = vy[a];
+      }
+      __syncwarp();
+    }
+    c_act += ss.actions; c_obs += ss.obs; c_idx += ss.nbr_idx; c_feat += ss.nbr_feat; c_cnt += ss.nbr_cnt;
+    c_adj += ss.adj; c_rew += ss.reward; c_cost += ss.cost; c_done += ss.done; c_asg += ss.assign;
+  }
+
+  if (live) {
+#pragma unroll
+    for (int a = 0; a < A; a++) {
+      T* s = p.agent_state + (env * N + g * A + a) * 4;
+      st2<T>(s, px[a], py[a]); st2<T>(s + 2, vx[a], vy[a]);
+    }
+    if (g == 0) {
+      p.t[env] = t_now;
+      if (auto_reset && ep != ep0) {
+#pragma unroll
+        for (int l = 0; l < L; l++) { T* m = p.lm_pos + (env * L + l) * 2; m[0] = mx[l]; m[1] = my[l]; }
+        p.episode[env] = ep;
+      }
+    }
+  }
+}
+
+}  // namespace gsm

@@ -13,6 +13,7 @@ static int env_int(const char* name, int dflt) {
 static bool has_spec(const HostParams& hp);
 static bool has_big(const HostParams& hp);
 static bool has_lane(const HostParams& hp);
+static bool has_team(const HostParams& hp);
 static int next_pow2(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
 int GSM_SFX(plan)(const HostParams& hp, LaunchPlan* plan) {
@@ -43,6 +44,7 @@ int GSM_SFX(plan)(const HostParams& hp, LaunchPlan* plan) {
   plan->grid = (hp.n_envs + plan->envs_per_cta - 1) / plan->envs_per_cta;
   if (plan->smem > 227 * 1024) return (int)cudaErrorInvalidValue;
   plan->spec = has_spec(hp) ? 1 : 0;
+  plan->team = has_team(hp) ? 1 : 0;   // polygon / line steps; observe stays on the specialised kernel
   // preference: lane-per-agent (N >= GSM_LANE_MIN_N) > specialised > CTA-per-env > generic
   plan->lane = has_lane(hp) ? 1 : 0;
   if (plan->lane) plan->spec = 0;
@@ -257,6 +259,54 @@ int GSM_SFX(launch_lane)(const HostParams& hp, const gsm_step_io& io, int n_step
   const int64_t grid = (hp.n_envs + g.envs_per_cta - 1) / g.envs_per_cta;
   k<<<(unsigned)grid, g.warps_per_cta * 32, smem, st>>>(kp, n_steps, ss);
   return (int)cudaGetLastError();
+}
+
+// ---- polygon / line kernel with the group-parallel assignment (gsm_kernels_team.cuh) -----------
+// (scenario, N, G): G lanes per env, N / G agents = assignment rows/columns per lane.
+#define GSM_TEAM_TABLE(X)                                                                     \
+  X(GSM_SCN_POLYGON, 3, 1) X(GSM_SCN_POLYGON, 4, 2) X(GSM_SCN_POLYGON, 5, 1) X(GSM_SCN_POLYGON, 6, 2) \
+  X(GSM_SCN_POLYGON, 12, 4)                                                                   \
+  X(GSM_SCN_LINE, 3, 1) X(GSM_SCN_LINE, 4, 2) X(GSM_SCN_LINE, 5, 1) X(GSM_SCN_LINE, 6, 2)     \
+  X(GSM_SCN_LINE, 12, 4)
+
+static bool has_team(const HostParams& hp) {
+  if (env_int("GSM_NO_TEAM", 0) != 0 || env_int("GSM_NO_SPEC", 0) != 0 || env_int("GSM_FORCE_P", 0) != 0 ||
+      env_int("GSM_FORCE_CTA_ENV", -1) >= 0 || env_int("GSM_SPEC_P", 0) != 0)
+    return false;
+#define X(S, n, gg) if (hp.scenario == S && hp.N == n) return true;
+  GSM_TEAM_TABLE(X)
+#undef X
+  return false;
+}
+
+template <int SCN, int N, int G>
+static int launch_team_one(const KParams<GSM_REAL>& kp, int n_steps, const StepStrides& ss, cudaStream_t st) {
+  constexpr int EPW = 32 / G, WPC = kTeamThreads / 32;
+  const int64_t grid = (kp.n_envs + EPW * WPC - 1) / (EPW * WPC);
+  const size_t smem = (size_t)WPC * EPW * team_env_bytes((int)sizeof(GSM_REAL), N);
+  auto k = env_team_kernel<GSM_REAL, SCN, N, G>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k<<<(unsigned)grid, kTeamThreads, smem, st>>>(kp, n_steps, ss);
+  return (int)cudaGetLastError();
+}
+
+int GSM_SFX(launch_team)(const HostParams& hp, const gsm_step_io& io, int n_steps,
+                         const RolloutStrides& rs, cudaStream_t st) {
+  if (!has_team(hp)) return -1;
+  if (hp.n_envs == 0) return 0;
+  KParams<GSM_REAL> kp;
+  fill_kparams(kp, hp, io, 0, nullptr, 0);
+  StepStrides ss;
+  ss.actions = rs.actions; ss.obs = rs.obs; ss.nbr_idx = rs.nbr_idx; ss.nbr_feat = rs.nbr_feat;
+  ss.nbr_cnt = rs.nbr_cnt; ss.adj = rs.adj; ss.reward = rs.reward; ss.cost = rs.cost;
+  ss.done = rs.done; ss.assign = rs.assign;
+#define X(S, n, gg) if (hp.scenario == S && hp.N == n) return launch_team_one<S, n, gg>(kp, n_steps, ss, st);
+  GSM_TEAM_TABLE(X)
+#undef X
+  return -1;
 }
 
 int GSM_SFX(launch_reset)(const HostParams& hp, uint64_t seed, const uint8_t* mask,

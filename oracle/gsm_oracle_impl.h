@@ -94,7 +94,9 @@ static void ORC(targets)(const gsm_config* c, const REAL* ag, const REAL* lm, in
       REAL dx = sx[k] - ag[4 * i], dy = sy[k] - ag[4 * i + 1];
       cost[i * N + k] = R_SQRT(dx * dx + dy * dy);
     }
-  ORC(lsa)(cost, N, assign);
+  /* non-finite costs (coincident entities -> NaN forces) are outside SPEC.md: identity, no crash */
+  if (ORC(lsa)(cost, N, assign) != 0)
+    for (int i = 0; i < N; i++) assign[i] = i;
   for (int i = 0; i < N; i++) { tx[i] = sx[assign[i]]; ty[i] = sy[assign[i]]; }
 }
 

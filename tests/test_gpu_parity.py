@@ -501,3 +501,85 @@ def test_rollout_auto_reset_matches_oracle_resets(name, N, kw, env_vars, monkeyp
     env.reset()
     assert (env.get_state()[0].cpu().numpy() == o.agent_state).all()
     env.close()
+
+
+def test_fixed_size_env_variants_and_spaces():
+    """MultiAgentEnv / MultiAgentConstrainEnv (reference readme.md:29-37): fixed-size views over
+    the same kernel; the graph env's per-agent space descriptors."""
+    from gs_marl_b200.environment import (MultiAgentEnv, MultiAgentConstrainEnv,
+                                          MultiAgentGraphConstrainEnv)
+    cfg = make_cfg("navigation", 3, "f64")
+    B = 8
+    o = _squeezed_start(cfg, B, 12)
+    a = random_actions(cfg, np.random.default_rng(0), (B,))
+    want = o.step(a)
+    flat_want = np.concatenate([want["obs"], want["nbr_feat"].reshape(B, 3, -1)], -1)
+    for cls in (MultiAgentConstrainEnv, MultiAgentEnv):
+        env = cls(cfg, B)
+        start = _squeezed_start(cfg, B, 12)
+        env.set_state(start.agent_state, start.landmark_pos, start.step_count)
+        out = env.step(a)
+        assert len(out) == (5 if cls is MultiAgentConstrainEnv else 4)
+        obs, rew = out[0], out[1]
+        assert tuple(obs.shape) == (B, 3, 6 + cfg.max_nbrs * 6)
+        np.testing.assert_allclose(obs.cpu().numpy(), flat_want, rtol=F64_RTOL, atol=F64_ATOL)
+        np.testing.assert_allclose(rew.cpu().numpy(), want["reward"], rtol=F64_RTOL, atol=F64_ATOL)
+        if cls is MultiAgentConstrainEnv:
+            assert (out[2].cpu().numpy() == want["cost"]).all()
+        assert tuple(env.reset().shape) == (B, 3, 6 + cfg.max_nbrs * 6)
+        env.close()
+    g = MultiAgentGraphConstrainEnv(cfg, B)
+    assert g.n == 3 and len(g.observation_space) == 3 and g.observation_space[0].shape == (6,)
+    assert g.node_observation_space[0].shape == (cfg.max_nbrs, 6) and g.action_space[0].n == 5
+    assert g.share_observation_space[0].shape == (18,)
+    g.close()
+    c = MultiAgentGraphConstrainEnv(make_cfg("navigation", 3, "f32", action_mode="continuous"), 4)
+    assert c.action_space[0].shape == (2,)
+    with pytest.raises(ValueError):
+        c.step(np.zeros((4, 3), np.float32))               # wrong action shape
+    c.close()
+
+
+@pytest.mark.parametrize("name,N", [("polygon", 3), ("polygon", 4), ("polygon", 5), ("polygon", 6), ("polygon", 12),
+                                    ("line", 3), ("line", 4), ("line", 5), ("line", 6), ("line", 12)])
+@pytest.mark.parametrize("kw", [{}, {"share_reward": True, "max_nbrs": 2}])
+def test_team_kernel_group_lsa_f64(name, N, kw):
+    """env_team_kernel (G lanes per env, N/G assignment rows per lane): fused 25 steps and single
+    steps against the oracle, plus a TIE-HEAVY start (all agents on one point, then agents exactly
+    on the slots in reversed order) where only scipy's scan order decides the permutation."""
+    cfg = make_cfg(name, N, "f64", **kw)
+    B, T = 70, 25
+    o = _squeezed_start(cfg, B, 17 + N)
+    # ambiguous optima without coincident entities: envs 0..9 agents halfway between consecutive
+    # slots (two equally good shifts), envs 10..19 agents exactly on the slots in reversed order
+    def slots_of(lm):
+        if name == "polygon":
+            return lm[:, :1, :] + cfg.polygon_radius * np.asarray(cfg.slot_table)[None]
+        f = np.asarray(cfg.slot_table)[:, 0][None, :, None]
+        return lm[:, :1, :] + f * (lm[:, 1:2, :] - lm[:, :1, :])
+    sl = slots_of(o.landmark_pos[:20])
+    if name == "polygon":
+        ang = (2 * np.arange(N) + 1) * np.pi / N
+        o.agent_state[:10, :, :2] = o.landmark_pos[:10, :1, :] + cfg.polygon_radius * np.stack([np.cos(ang), np.sin(ang)], -1)[None]
+    else:
+        mid = 0.5 * (sl[:10] + np.roll(sl[:10], -1, axis=1))
+        mid[:, -1] = sl[:10, -1] + 0.5 * (sl[:10, -1] - sl[:10, -2])
+        o.agent_state[:10, :, :2] = mid
+    o.agent_state[10:20, :, :2] = sl[10:20, ::-1, :]
+    o.agent_state[:20, :, 2:] = 0
+    s0 = o.agent_state.copy()
+    env = _env(cfg, B)
+    env.set_state(o.agent_state, o.landmark_pos, o.step_count)
+    acts = random_actions(cfg, np.random.default_rng(N), (T, B))
+    acts[0] = 0                                               # first step: nobody moves -> exact ties
+    wants = [{k: v.copy() for k, v in o.step(acts[t]).items()} for t in range(T)]
+    roll = _np(env.rollout(acts))
+    assert env.kernel_launches == 1
+    for t in range(T):
+        assert_match({k: roll[k][t] for k in OUT_KEYS}, wants[t], rtol=F64_RTOL, atol=F64_ATOL,
+                     ctx=f"{name}{N} team fused t={t}")
+    env.set_state(s0, o.landmark_pos, np.zeros(B, np.int32))
+    for t in range(2):
+        env.step(acts[t])
+        assert_match(_np(env.buf), wants[t], rtol=F64_RTOL, atol=F64_ATOL, ctx=f"{name}{N} team step t={t}")
+    env.close()
