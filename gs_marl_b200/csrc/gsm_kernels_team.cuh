@@ -38,27 +38,31 @@ __device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int ba
   const T INF = r_inf<T>();
   T u[A], v[A], spc[A];
   int path[A], r4c[A], pos[A];
+  bool inr[A];                                            // column still in scipy's `remaining`
+  const T* Cg = C + g * A;                                // my A columns of a cost row
 #pragma unroll
-  for (int a = 0; a < A; a++) { u[a] = 0; v[a] = 0; path[a] = -1; r4c[a] = -1; c4r[a] = -1; spc[a] = INF; pos[a] = 0; }
+  for (int a = 0; a < A; a++) { u[a] = 0; v[a] = 0; path[a] = -1; r4c[a] = -1; c4r[a] = -1; spc[a] = INF; pos[a] = 0; inr[a] = false; }
   for (int cur = 0; cur < N; cur++) {
     T minval = 0;
     int i = cur, nrem = N, sink = live ? -1 : 0;
-    unsigned inrem = live ? ((1u << A) - 1u) : 0u, sr = 0, sc = 0;
+    unsigned sr = 0, sc = 0;
 #pragma unroll
-    for (int a = 0; a < A; a++) { spc[a] = INF; pos[a] = N - 1 - (g * A + a); }
+    for (int a = 0; a < A; a++) { spc[a] = INF; pos[a] = N - 1 - (g * A + a); inr[a] = live; }
     for (int iter = 0; iter < N && __any_sync(FULL, sink == -1); iter++) {
       const bool run = sink == -1;
       const int ig = i / A, il = i - ig * A;
       if (run && ig == g) sr |= 1u << il;
       const T u_i = shfl(FULL, sel<T, A>(u, il), base + ig);
+      const T* Ci = Cg + i * N;
       T lo = INF;
 #pragma unroll
       for (int a = 0; a < A; a++) {
-        if (run && ((inrem >> a) & 1u)) {
-          const T r = minval + C[i * N + g * A + a] - u_i - v[a];
+        if (run && inr[a]) {
+          const T r = minval + Ci[a] - u_i - v[a];
           if (r < spc[a]) { path[a] = i; spc[a] = r; }
         }
-        if ((inrem >> a) & 1u) lo = spc[a] < lo ? spc[a] : lo;
+        const T cand = inr[a] ? spc[a] : INF;
+        lo = cand < lo ? cand : lo;
       }
 #pragma unroll
       for (int m = G / 2; m >= 1; m >>= 1) {
@@ -70,11 +74,9 @@ __device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int ba
       int best = -1;
 #pragma unroll
       for (int a = 0; a < A; a++) {
-        if (((inrem >> a) & 1u) && spc[a] == lo) {
-          const int key = r4c[a] == -1 ? 64 + pos[a] : 31 - pos[a];
-          const int packed = (key << 6) | (g * A + a);
-          best = packed > best ? packed : best;
-        }
+        const int key = r4c[a] == -1 ? 64 + pos[a] : 31 - pos[a];
+        const int packed = (inr[a] && spc[a] == lo) ? ((key << 6) | (g * A + a)) : -1;
+        best = packed > best ? packed : best;
       }
 #pragma unroll
       for (int m = G / 2; m >= 1; m >>= 1) {
@@ -88,11 +90,12 @@ __device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int ba
       if (run && best >= 0) {
         minval = lo;
         if (r4c_j == -1) sink = j; else i = r4c_j;
-        if (jg == g) { sc |= 1u << jl; inrem &= ~(1u << jl); }
         nrem--;
 #pragma unroll
-        for (int a = 0; a < A; a++)
-          if (((inrem >> a) & 1u) && pos[a] == nrem) pos[a] = selpos;
+        for (int a = 0; a < A; a++) {
+          if (jg == g && jl == a) { sc |= 1u << a; inr[a] = false; }
+          if (inr[a] && pos[a] == nrem) pos[a] = selpos;
+        }
       }
     }
     // dual update (col4row as it was before this augmentation)
