@@ -38,7 +38,7 @@ ROLLOUT_T = 25      # steps fused per launch (rollout-buffer slots)
 EPISODE_LEN = 25    # envs are re-drawn in-kernel every EPISODE_LEN steps
 SPEC_STATUS = ("declared model (SPEC.md) with UNVERIFIED constants; GS-MARL env sources withheld, "
                "parity with the reference unpinned")
-METRIC = "agent-steps/sec (graph obs+reward+cost)"
+METRIC = "agent-steps/sec (graph obs+reward+cost) at 1/2/4/8 B200; % HBM roofline"   # BASELINE.json
 UNIT = "agent-steps/s"
 
 
@@ -111,6 +111,25 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
                 "samples": len(sm), "window": window}
+
+
+def pin_to_gpu_numa(gpu_index):
+    """Bind this rank to the CPUs NVML reports as local to its GPU, before any pinned host memory
+    is allocated, so that the e2e arena and the copy threads sit on the GPU's own socket."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {w * 64 + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to gpu {gpu_index}"
+    except Exception as e:        # topology unknown: leave the affinity alone
+        return f"unpinned ({type(e).__name__})"
+    return "unpinned"
 
 
 def measured_peak():
@@ -269,6 +288,7 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa(local)
     if world > 1:
         # NCCL prints its version banner to stdout when the first communicator is built; stdout
         # must carry exactly one JSON line, so fd 1 points at stderr until NCCL is up.
@@ -289,7 +309,7 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    K, W, T = args.steps, args.warmup, ROLLOUT_T
+    K, W, T = args.steps, args.warmup, args.rollout_t
     spec_p = os.environ.get("GSM_SPEC_P", "4 (default)")
     cfg = scenarios.load("navigation").make_world(N_AGENTS, dtype="f32", episode_length=EPISODE_LEN)
     env = MultiAgentGraphConstrainEnv(cfg, args.envs, device=local, env_offset=rank * args.envs, seed=1)
@@ -423,7 +443,8 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": args.envs * N_AGENTS * Ke * world / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "api": "GraphVecEnv.step -> gsm_step_host (pinned arena; 1 H2D + 1 kernel + 1 D2H)"},
+                    "api": "GraphVecEnv.step -> gsm_step_host (pinned arena; 1 H2D + 1 kernel + 1 D2H)",
+                    "host_affinity": numa},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(),
@@ -514,6 +535,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--rollout-t", type=int, default=ROLLOUT_T, help="steps fused per launch")
     ap.add_argument("--closed-loop-steps", type=int, default=200)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--ref-budget", type=float, default=90.0)
