@@ -20,8 +20,11 @@ us = e0.elapsed_time(e1) * 1e3 / (5 * T)
 gbs = cfg.bytes_per_agent_step() * 3 * n / (us * 1e-6) / 1e9
 print("%%d envs  %%8.2f us/step  %%7.1f GB/s  %%5.1f%%%% of 6546" %% (n, us, gbs, 100 * gbs / 6546.2))
 ''' % ROOT
-for n in (65536, 262144, 1048576):
-    for P in (8, 4, 2, 1):
-        env = dict(os.environ, GSM_SPEC_P=str(P))
+variants = [("spec P=%d" % P, {"GSM_SPEC_P": str(P)}) for P in (8, 4, 2, 1)] + [("lane", {"GSM_LANE_MIN_N": "3"})]
+if len(sys.argv) > 1:
+    variants = [v for v in variants if v[0].split()[0] in sys.argv[1:] or v[0] in sys.argv[1:]]
+for n in (16384, 65536, 262144, 1048576):
+    for name, ev in variants:
+        env = dict(os.environ, **ev)
         out = subprocess.run([sys.executable, "-c", code, str(n)], env=env, capture_output=True, text=True)
-        print(f"P={P}", out.stdout.strip() or out.stderr.strip()[-300:], flush=True)
+        print(f"{name:9s}", out.stdout.strip() or out.stderr.strip()[-300:], flush=True)
