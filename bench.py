@@ -319,14 +319,18 @@ def run_gpu(args):
     ring = {k: env._alloc(k, (T,)) for k in env.OUTPUTS}       # rollout buffer, T slots
     ring_bytes = sum(v.numel() * v.element_size() for v in ring.values())
 
+    import ctypes as C
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    io_full = env._make_io(ring, acts)                    # slot 0 of the [T][...] rollout buffers
+    env._check(env.lib.gsm_set_auto_reset(env._h, 1))
+
     def run_steps(n):
-        """n env steps: fused rollouts of T steps; envs finish an episode every T steps and are
-        re-drawn inside the kernel (gsm_set_auto_reset), so there is no other launch."""
+        """n env steps through the C ABI: fused rollouts of T steps (gsm_rollout); envs finish an
+        episode every EPISODE_LEN steps and are re-drawn inside the kernel, no other launch."""
         done = 0
         while done < n:
             m = min(T, n - done)
-            env.rollout(acts[:m], out={k: v[:m] for k, v in ring.items()} if m < T else ring,
-                        auto_reset=True)
+            env._check(env.lib.gsm_rollout(env._h, m, C.byref(io_full), stream))
             done += m
 
     sampler = ClockSampler(local); sampler.start()
@@ -358,6 +362,21 @@ def run_gpu(args):
     k1.record()
     torch.cuda.synchronize()
     kern_ms = k0.elapsed_time(k1) / (reps * T)
+
+    # ---- un-fused API: one gsm_step launch per env step (what a policy-in-the-loop caller uses) ----
+    io_slots = [env._make_io({k: v[sidx] for k, v in ring.items()}, acts[sidx]) for sidx in range(T)]
+    env._check(env.lib.gsm_set_auto_reset(env._h, 0))
+    n_single = max(T, min(2000, K))
+    for sidx in range(T):
+        env._check(env.lib.gsm_step(env._h, C.byref(io_slots[sidx]), stream))
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for q in range(n_single):
+        env._check(env.lib.gsm_step(env._h, C.byref(io_slots[q % T]), stream))
+    s1.record()
+    torch.cuda.synchronize()
+    single_us = s0.elapsed_time(s1) * 1e3 / n_single
 
     # ---- same kernel at a batch that saturates the GPU (explains the small-batch fraction) -------
     large = None
@@ -456,6 +475,9 @@ def run_gpu(args):
                          "frac_fused_exact": achieved_fused / peak,
                          "bytes_per_agent_step": cfg.bytes_per_agent_step(), "peak_source": peak_src,
                          "note": "layout is the declared one of SPEC.md §6 (reference layout unknown)"},
+            "single_step_api": {"value": args.envs * N_AGENTS * world / (single_us * 1e-6), "unit": UNIT,
+                                "us_per_step": single_us, "steps": n_single,
+                                "note": "gsm_step, one kernel launch per env step, outputs to rotating slots"},
             "final_stats": totals,
         }
         if world == 1 and not args.no_cpu:
@@ -511,18 +533,39 @@ def closed_loop(env, cfg, n_steps, dev):
     for _ in range(10):
         obs, graph, *_ = env.step(act(obs, graph))
     torch.cuda.synchronize()
+    # one closed-loop iteration (policy forward + sampling + gsm_step) captured in a CUDA graph:
+    # env.step reads/writes fixed buffers, so replaying the graph advances the rollout
+    mode = "CUDA graph of one policy+env iteration"
+    try:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                env.step(act(obs, graph))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            env.step(act(obs, graph))
+        step = g.replay
+    except Exception as e:                                # capture unsupported: eager fallback
+        mode = f"eager ({type(e).__name__})"
+
+        def step():
+            env.step(act(obs, graph))
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(n_steps):
-        obs, graph, rew, cost, done, infos = env.step(act(obs, graph))
+        step()
         if (s + 1) % EPISODE_LEN == 0:
-            obs, graph = env.reset()
+            env.reset()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     return {"value": env.n_envs * cfg.n_agents * n_steps / (ms * 1e-3), "unit": UNIT, "steps": n_steps,
             "ms_per_step": ms / n_steps,
-            "policy": f"random-init graph-attention policy, hidden {H}, plain PyTorch eager (library kernels)"}
+            "policy": f"random-init graph-attention policy, hidden {H}, plain PyTorch (library kernels); {mode}"}
 
 
 def main():
@@ -536,7 +579,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--rollout-t", type=int, default=ROLLOUT_T, help="steps fused per launch")
-    ap.add_argument("--closed-loop-steps", type=int, default=200)
+    ap.add_argument("--closed-loop-steps", type=int, default=1000)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--ref-budget", type=float, default=90.0)
     ap.add_argument("--no-cpu", action="store_true")
