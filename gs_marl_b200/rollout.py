@@ -1,0 +1,84 @@
+"""Device-resident rollout buffer and collect loop — the rows SURVEY.md §8 marks "next":
+f1 `runner/mpe_runner.py` collect loop (GSMARL.egg-info/SOURCES.txt:28) and f2
+`utils/graph_separated_buffer.py` insert path (SOURCES.txt:33).  Both are withheld in the
+reference; this is the minimal B200-side counterpart: the env kernel writes every step's
+outputs DIRECTLY into slot t of the buffer (gsm_step with the io pointers aimed at the slot),
+so "insert" is not a copy, and nothing leaves the GPU between policy and env.
+
+Layout (time-major like the lineage's buffers, agents kept as a dimension instead of one
+buffer per agent): observations/graph have T+1 slots (slot t = what the policy sees before
+action t), rewards/costs/dones/actions have T.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable
+
+import torch
+
+from . import abi
+from .environment import MultiAgentGraphConstrainEnv, _TORCH_DT
+
+_OBS_KEYS = ("obs", "nbr_idx", "nbr_feat", "nbr_cnt", "adj", "assign")
+_STEP_KEYS = ("reward", "cost", "done")
+
+
+class GraphRolloutBuffer:
+    def __init__(self, env: MultiAgentGraphConstrainEnv, episode_length: int):
+        self.env, self.T = env, int(episode_length)
+        sh = env._shapes
+        dev = env.device
+        self.data = {}
+        for k in _OBS_KEYS:
+            dt, shape = sh[k]
+            self.data[k] = torch.zeros((self.T + 1,) + tuple(shape), dtype=_TORCH_DT[dt], device=dev)
+        for k in _STEP_KEYS + ("actions",):
+            dt, shape = sh[k]
+            self.data[k] = torch.zeros((self.T,) + tuple(shape), dtype=_TORCH_DT[dt], device=dev)
+        self.step = 0
+        # one pre-built io struct per step: outputs of step t land in obs-slot t+1 / step-slot t
+        self._io = []
+        for t in range(self.T):
+            io = abi.GsmStepIO()
+            io.actions = self.data["actions"][t].data_ptr()
+            for k in _OBS_KEYS:
+                setattr(io, k, self.data[k][t + 1].data_ptr())
+            for k in _STEP_KEYS:
+                setattr(io, k, self.data[k][t].data_ptr())
+            self._io.append(io)
+        io0 = abi.GsmStepIO()
+        for k in _OBS_KEYS:
+            setattr(io0, k, self.data[k][0].data_ptr())
+        self._io_reset = io0
+
+    def __getitem__(self, k):
+        return self.data[k]
+
+    def graph(self, t: int) -> dict:
+        return {k: self.data[k][t] for k in ("nbr_idx", "nbr_feat", "nbr_cnt", "adj")}
+
+    def reset_env(self):
+        """env.reset() with the first observation written straight into slot 0."""
+        e = self.env
+        with torch.cuda.device(e.device):
+            e._check(e.lib.gsm_reset(e._h, e._seed, None, 1, C.byref(self._io_reset), e._stream()))
+        self.step = 0
+
+    def after_update(self):
+        """Lineage buffers copy the last observation to slot 0 after an update."""
+        for k in _OBS_KEYS:
+            self.data[k][0].copy_(self.data[k][self.T])
+        self.step = 0
+
+
+def collect(env: MultiAgentGraphConstrainEnv, policy: Callable, buf: GraphRolloutBuffer) -> GraphRolloutBuffer:
+    """One rollout of buf.T steps: actions = policy(obs_t, graph_t) -> [n_envs, N(,2)] device
+    tensor; the env step writes reward/cost/done of step t and obs/graph of t+1 into the buffer."""
+    with torch.cuda.device(env.device):
+        stream = env._stream()
+        for t in range(buf.T):
+            a = policy(buf.data["obs"][t], buf.graph(t))
+            buf.data["actions"][t].copy_(a)
+            env._check(env.lib.gsm_step(env._h, C.byref(buf._io[t]), stream))
+    buf.step = buf.T
+    return buf

@@ -583,3 +583,44 @@ def test_team_kernel_group_lsa_f64(name, N, kw):
         env.step(acts[t])
         assert_match(_np(env.buf), wants[t], rtol=F64_RTOL, atol=F64_ATOL, ctx=f"{name}{N} team step t={t}")
     env.close()
+
+
+def test_rollout_buffer_collect_is_zero_copy_and_matches_step():
+    """collect() with the kernel writing into the rollout buffer's slots gives
+    exactly what step()-then-copy gives, and what the oracle gives."""
+    from gs_marl_b200.rollout import GraphRolloutBuffer, collect
+    cfg = make_cfg("polygon", 4, "f64", episode_length=50)
+    B, T = 33, 9
+    o = _squeezed_start(cfg, B, 21)
+    env = _env(cfg, B)
+    env.set_state(o.agent_state, o.landmark_pos, o.step_count)
+    buf = GraphRolloutBuffer(env, T)
+    env.observe()
+    for k in ("obs", "nbr_idx", "nbr_feat", "nbr_cnt", "adj", "assign"):
+        buf[k][0].copy_(env.buf[k])
+
+    def policy(obs, graph):                        # deterministic, depends on what it is shown
+        s = (obs[..., 2] * 7.0 + graph["nbr_cnt"].to(obs.dtype)).floor().to(torch.int64)
+        return (s % 5).to(torch.int32)
+
+    launches0 = env.kernel_launches
+    collect(env, policy, buf)
+    assert env.kernel_launches - launches0 == T
+    # same policy against the oracle
+    want0 = o.observe()
+    obs_t = torch.as_tensor(want0["obs"]).cuda()
+    cnt_t = torch.as_tensor(want0["nbr_cnt"]).cuda()
+    for t in range(T):
+        a = policy(obs_t, {"nbr_cnt": cnt_t}).cpu().numpy()
+        assert (buf["actions"][t].cpu().numpy() == a).all(), t
+        w = o.step(a)
+        got = {k: buf[k][t + 1].cpu().numpy() for k in ("obs", "nbr_idx", "nbr_feat", "nbr_cnt", "assign")}
+        got["adj"] = buf["adj"][t + 1].cpu().numpy().view(np.uint32)
+        got.update({k: buf[k][t].cpu().numpy() for k in ("reward", "cost", "done")})
+        assert_match(got, w, rtol=F64_RTOL, atol=F64_ATOL, ctx=f"collect t={t}")
+        obs_t, cnt_t = buf["obs"][t + 1], buf["nbr_cnt"][t + 1]
+    buf.after_update()
+    assert torch.equal(buf["obs"][0], buf["obs"][T]) and buf.step == 0
+    buf.reset_env()
+    assert torch.equal(buf["obs"][0][..., 2:4], env.get_state()[0][..., :2])
+    env.close()
