@@ -624,3 +624,44 @@ def test_rollout_buffer_collect_is_zero_copy_and_matches_step():
     buf.reset_env()
     assert torch.equal(buf["obs"][0][..., 2:4], env.get_state()[0][..., :2])
     env.close()
+
+
+@pytest.mark.parametrize("name,N,kw,env_vars", [
+    ("navigation", 3, {}, {}), ("navigation", 3, {}, {"GSM_SPEC_P": "8"}), ("navigation", 3, {}, {"GSM_SPEC_P": "1"}),
+    ("navigation", 6, {}, {}), ("navigation", 12, {"max_nbrs": 7}, {}), ("navigation", 40, {"max_nbrs": 16}, {}),
+    ("navigation", 24, {"max_nbrs": 16}, {"GSM_NO_LANE": "1"}),
+    ("navigation", 33, {"n_obstacles": 0, "max_nbrs": 65}, {"GSM_NO_LANE": "1"}),
+    ("polygon", 6, {}, {}), ("polygon", 12, {"max_nbrs": 5}, {}), ("line", 5, {}, {}),
+    ("polygon", 6, {}, {"GSM_SPEC_P": "1"}), ("line", 4, {}, {"GSM_NO_SPEC": "1"}),
+])
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_no_kernel_writes_outside_its_buffers(name, N, kw, env_vars, dtype, monkeypatch):
+    """compute-sanitizer is closed on this pool, so: every output tensor of a fused rollout, a
+    single step and a masked reset sits between guard bands that must stay untouched, with an
+    env count that leaves ragged tail warps / CTAs."""
+    for k, v in env_vars.items():
+        monkeypatch.setenv(k, v)
+    cfg = make_cfg(name, N, dtype, episode_length=3, **kw)
+    B, T, G = 37, 5, 4096                                   # G guard bytes on each side
+    env = _env(cfg, B, seed=3)
+    env.reset()
+    raw, out = {}, {}
+    for k in env.OUTPUTS:
+        dt, shape = env._shapes[k]
+        tdt = env.buf[k].dtype
+        n = T * int(np.prod(shape)) * env.buf[k].element_size()
+        raw[k] = torch.full((n + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+        out[k] = raw[k][G:G + n].view(tdt).view((T,) + tuple(shape))
+    acts = torch.as_tensor(random_actions(cfg, np.random.default_rng(0), (T, B))).cuda()
+    env.rollout(acts, out=out, auto_reset=True)
+    io = env._make_io({k: v[0] for k, v in out.items()}, acts[0].contiguous())
+    env._check(env.lib.gsm_step(env._h, C.byref(io), env._stream()))
+    mask = torch.as_tensor(np.arange(B) % 3 == 0).to(torch.uint8).cuda()
+    env._check(env.lib.gsm_reset(env._h, 3, mask.data_ptr(), 1, C.byref(io), env._stream()))
+    torch.cuda.synchronize()
+    for k, r in raw.items():
+        assert bool((r[:G] == 0xA5).all()) and bool((r[-G:] == 0xA5).all()), f"{k}: guard band overwritten"
+        if k in ("obs", "reward"):
+            assert torch.isfinite(out[k].double()).all(), k
+    assert int(out["nbr_cnt"].min()) >= 0 and int(out["nbr_cnt"].max()) <= cfg.max_nbrs
+    env.close()
