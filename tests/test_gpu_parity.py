@@ -665,3 +665,43 @@ def test_no_kernel_writes_outside_its_buffers(name, N, kw, env_vars, dtype, monk
             assert torch.isfinite(out[k].double()).all(), k
     assert int(out["nbr_cnt"].min()) >= 0 and int(out["nbr_cnt"].max()) <= cfg.max_nbrs
     env.close()
+
+
+@pytest.mark.parametrize("name,N,B,kw", [("navigation", 3, 16384, {}), ("polygon", 12, 16384, {}),
+                                         ("line", 6, 16384, {}), ("navigation", 96, 4096, {"max_nbrs": 32}),
+                                         ("navigation", 12, 8192, {})])
+def test_translation_invariance_at_full_size(name, N, B, kw):
+    """Size-independent property at BASELINE's full env counts (no oracle needed): shifting every
+    entity of every env by one vector changes nothing but the absolute positions in obs —
+    neighbour lists, adjacency, costs, dones and assignments bit-identical (the shift is a
+    power of two and positions are pre-rounded so that every difference is exact), rewards and
+    relative features identical."""
+    cfg = make_cfg(name, N, "f64", **kw)
+    from oracle import gsm_oracle as O
+    o = O.OracleEnv(cfg, B)
+    o.reset(77)
+    q = 2.0 ** -20                                       # positions on a grid: shifted sums stay exact
+    ag = np.round(o.agent_state * 0.6 / q) * q
+    lm = np.round(o.landmark_pos * 0.6 / q) * q
+    ag[..., 2:] = 0
+    shift = np.array([8.0, -4.0])
+    acts = random_actions(cfg, np.random.default_rng(5), (B,))
+    outs = []
+    for s in (np.zeros(2), shift):
+        env = _env(cfg, B)
+        a2 = ag.copy(); a2[..., :2] += s
+        env.set_state(a2, lm + s, np.zeros(B, np.int32))
+        env.observe()
+        outs.append(_np({k: v.clone() for k, v in env.buf.items()}))
+        env.close()
+    a, b = outs
+    for k in ("nbr_idx", "nbr_cnt", "adj", "assign"):
+        assert (a[k] == b[k]).all(), k
+    assert (a["nbr_feat"] == b["nbr_feat"]).all()
+    assert (a["obs"][..., :2] == b["obs"][..., :2]).all()
+    if name == "navigation":
+        assert (a["obs"][..., 4:] == b["obs"][..., 4:]).all()
+    else:       # slot = marker + R * unit is rounded after the shift: equal to an ulp of the shifted value
+        np.testing.assert_allclose(a["obs"][..., 4:], b["obs"][..., 4:], rtol=0, atol=4e-15)
+    assert (b["obs"][..., 2:4] - a["obs"][..., 2:4] == shift).all()
+    assert a["nbr_cnt"].sum() > 0
