@@ -705,3 +705,35 @@ def test_translation_invariance_at_full_size(name, N, B, kw):
         np.testing.assert_allclose(a["obs"][..., 4:], b["obs"][..., 4:], rtol=0, atol=4e-15)
     assert (b["obs"][..., 2:4] - a["obs"][..., 2:4] == shift).all()
     assert a["nbr_cnt"].sum() > 0
+
+
+def test_graph_vec_env_host_auto_reset():
+    """numpy drop-in with auto_reset: after `done` the returned obs/graph rows are those of the
+    freshly drawn episode, reward/cost/done keep the terminal step's values."""
+    from gs_marl_b200.env_wrappers import GraphVecEnv
+    from oracle import gsm_oracle as O
+    cfg = make_cfg("navigation", 3, "f64", episode_length=2)
+    B = 17
+    vec = GraphVecEnv(cfg, B, auto_reset=True, seed=4)
+    o = O.OracleEnv(cfg, B)
+    o.reset(4)
+    obs, graph = vec.reset()
+    assert (obs == o.observe()["obs"]).all()
+    rng = np.random.default_rng(0)
+    for t in range(1, 5):
+        a = random_actions(cfg, rng, (B,))
+        want = o.step(a)
+        obs, graph, rew, cost, done, infos = vec.step(a)
+        np.testing.assert_allclose(rew, want["reward"], rtol=F64_RTOL, atol=F64_ATOL)
+        assert (cost == want["cost"]).all() and (done == want["done"]).all()
+        if t % 2 == 0:
+            assert done.all()
+            o.reset(4)
+            w0 = o.observe()
+            np.testing.assert_allclose(obs, w0["obs"], rtol=F64_RTOL, atol=F64_ATOL)
+            assert (graph["nbr_idx"] == w0["nbr_idx"]).all()
+        else:
+            np.testing.assert_allclose(obs, want["obs"], rtol=F64_RTOL, atol=F64_ATOL)
+    ag, lm, tt = vec.get_state()
+    assert (tt == 0).all() and (ag == o.agent_state).all()
+    vec.close()
