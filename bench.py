@@ -350,18 +350,23 @@ def run_gpu(args):
     n_resets = K // EPISODE_LEN
     clocks = sampler.stop(wall0, wall1)
 
-    # dominant kernel alone (plain variant, no auto-reset code): CUDA events on the same stream
-    env.reset()
-    env.rollout(acts, out=ring, auto_reset=False)
-    torch.cuda.synchronize()
-    reps = max(2, min(40, K // T))
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(reps):
-        env.rollout(acts, out=ring, auto_reset=False)
-    k1.record()
-    torch.cuda.synchronize()
-    kern_ms = k0.elapsed_time(k1) / (reps * T)
+    # dominant kernel alone, back to back on the same stream, CUDA events: the variant of the timed
+    # region (compiled-in auto-reset, MODE 2) and the plain one (MODE 0)
+    def time_rollouts(auto):
+        env.reset()
+        env.rollout(acts, out=ring, auto_reset=auto)
+        torch.cuda.synchronize()
+        reps = max(2, min(40, K // T))
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(reps):
+            env._check(env.lib.gsm_rollout(env._h, T, C.byref(io_full), stream))
+        k1.record()
+        torch.cuda.synchronize()
+        return k0.elapsed_time(k1) / (reps * T)
+    kern_ms = time_rollouts(True)
+    kern_plain_ms = time_rollouts(False)
+    env._check(env.lib.gsm_set_auto_reset(env._h, 1))
 
     # ---- un-fused API: one gsm_step launch per env step (what a policy-in-the-loop caller uses) ----
     io_slots = [env._make_io({k: v[sidx] for k, v in ring.items()}, acts[sidx]) for sidx in range(T)]
@@ -467,8 +472,9 @@ def run_gpu(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(),
-                         "kernel": f"gsm::env_steps_kernel<float, NAVIGATION, 3, 6, P={spec_p}> "
+                         "kernel": f"gsm::env_steps_kernel<float, NAVIGATION, 3, 6, P={spec_p}, MODE=2 (auto-reset)> "
                                    f"(one launch = {T} fused steps; achieved is per step)",
+                         "plain_variant_step_us": kern_plain_ms * 1e3,
                          "launch_us": kern_ms * 1e3 * T, "step_us": kern_ms * 1e3,
                          "algorithmic_bytes_per_launch": bytes_launch * T,
                          "algorithmic_bytes_per_step": bytes_launch,

@@ -175,10 +175,14 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   // obs: lane sub (and sub + P, ...) writes pair `part` of (vx,vy | px,py | gx,gy)
   unsigned char* c_obs = (unsigned char*)(p.obs + row * GSM_OBS_DIM + 2 * (sub % 3));
   constexpr int OBS_PASSES = (3 + P - 1) / P;
-  // per-agent scalars.  P >= 8: one output per lane ("roles": 0 cnt, 1 adj word 0, 2 reward,
-  // 3 cost, 4 assign, 5 done) so that a step issues one 32-bit, one real-sized and one byte
-  // store for all six.  P < 8: lane sub == 0 walks six cursors.
-  constexpr bool ROLES = P >= 8 && W == 1;
+  // per-agent scalars by "lane roles": lane sub of the agent's group owns one output
+  // (0 cnt, 1 adj word 0, 2 reward, 3 cost; with P >= 8 also 4 assign, 5 done), so a step issues
+  // one 32-bit (fp64: plus one 64-bit) store for them instead of one store per output on lane 0.
+  // With P == 4 lane 0 additionally walks the assign and done cursors; P < 4 walks all six.
+  // (measured per variant on nav-3, P = 4: the plain MODE 0 loop is 3 % faster with lane 0 walking
+  // six cursors, the auto-reset MODE 2 loop 10 % faster with 4 roles — register pressure differs)
+  constexpr bool ROLES = (P >= 8 || (P >= 4 && MODE == 2)) && W == 1;
+  constexpr int NROLES = P >= 8 ? 6 : 4;
   unsigned char* c_role = nullptr;
   int64_t role_stride = 0;
   unsigned char *c_cnt = nullptr, *c_adj = nullptr, *c_rew = nullptr, *c_cost = nullptr,
@@ -189,10 +193,11 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       case 1: c_role = (unsigned char*)(p.adj + row); role_stride = ss.adj; break;
       case 2: c_role = (unsigned char*)(p.reward + row); role_stride = ss.reward; break;
       case 3: c_role = (unsigned char*)(p.cost + row); role_stride = ss.cost; break;
-      case 4: c_role = (unsigned char*)(p.assign + row); role_stride = ss.assign; break;
-      case 5: c_role = (unsigned char*)(p.done + row); role_stride = ss.done; break;
+      case 4: if (NROLES > 4) { c_role = (unsigned char*)(p.assign + row); role_stride = ss.assign; } break;
+      case 5: if (NROLES > 4) { c_role = (unsigned char*)(p.done + row); role_stride = ss.done; } break;
       default: break;
     }
+    if (NROLES == 4) { c_asg = (unsigned char*)(p.assign + row); c_done = (unsigned char*)(p.done + row); }
   } else {
     c_cnt = (unsigned char*)(p.nbr_cnt + row); c_adj = (unsigned char*)(p.adj + row * W);
     c_rew = (unsigned char*)(p.reward + row); c_cost = (unsigned char*)(p.cost + row);
@@ -391,13 +396,14 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         if (sizeof(T) == 4) {
           const uint32_t v = ((uint32_t)cnt & rm0) | ((uint32_t)ebits & rm1) | (__float_as_uint((float)r) & rm2) |
                              (__float_as_uint((float)ncol) & rm3) | ((uint32_t)asg & rm4);
-          if (OBS ? (sub == 0 || sub == 1 || sub == 4) : (sub < 5)) *(uint32_t*)c_role = v;
+          if (OBS ? (sub == 0 || sub == 1 || (NROLES > 4 && sub == 4)) : (sub < (NROLES > 4 ? 5 : 4))) *(uint32_t*)c_role = v;
         } else {
           const uint32_t v = ((uint32_t)cnt & rm0) | ((uint32_t)ebits & rm1) | ((uint32_t)asg & rm4);
-          if (sub == 0 || sub == 1 || sub == 4) *(uint32_t*)c_role = v;
+          if (sub == 0 || sub == 1 || (NROLES > 4 && sub == 4)) *(uint32_t*)c_role = v;
           if (!OBS && (sub == 2 || sub == 3)) *(T*)c_role = sub == 2 ? r : (T)ncol;
         }
-        if (!OBS && sub == 5) *c_role = dn;
+        if (NROLES > 4) { if (!OBS && sub == 5) *c_role = dn; }
+        else if (sub == 0) { *(int32_t*)c_asg = asg; if (!OBS) *c_done = dn; }
       } else if (sub == 0) {
         *(int32_t*)c_cnt = cnt;
         *(uint32_t*)c_adj = (uint32_t)ebits;
@@ -437,8 +443,10 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     }
     // advance the cursors to the next slot of the rollout buffers
     c_idx += ss.nbr_idx; c_feat += ss.nbr_feat; c_obs += ss.obs;
-    if (ROLES) c_role += role_stride;
-    else {
+    if (ROLES) {
+      c_role += role_stride;
+      if (NROLES == 4) { c_asg += ss.assign; c_done += ss.done; }
+    } else {
       c_cnt += ss.nbr_cnt; c_adj += ss.adj; c_rew += ss.reward; c_cost += ss.cost;
       c_asg += ss.assign; c_done += ss.done;
     }
