@@ -119,7 +119,11 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   }
   __syncthreads();
   int nc = 0;
-  for (int e = 0; e < E; e++) nc += (p.eflag[e] & 1);
+  T max_size = 0;
+  for (int e = 0; e < E; e++) { nc += (p.eflag[e] & 1); const T sz = p.size[e]; max_size = sz > max_size ? sz : max_size; }
+  // every contact distance below the sensing radius: a colliding pair is a neighbour candidate
+  // anyway, so the candidate sweep needs one squared-distance test per pair instead of two
+  const bool col_in_nb = ((T)2 * max_size) * (T)1.0001 < p.Rs;
 
   const int ii = active ? i : 0;
   T px = ent[ii].x, py = ent[ii].y, vx = vel[2 * ii], vy = vel[2 * ii + 1];
@@ -260,8 +264,11 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
             const EntT q = ent[e0 + g0 + k];
             const T dx = q.x - px, dy = q.y - py;
             const T d2 = dx * dx + dy * dy;
-            const T dm = size_i + q.size;
-            if (Prec<T>::kCut ? (d2 < Rs2 || d2 < dm * dm * (T)1.000001) : (e0 + g0 + k < E)) m8 |= 1u << k;
+            bool c;
+            if (!Prec<T>::kCut) c = e0 + g0 + k < E;
+            else if (col_in_nb) c = d2 < Rs2;
+            else { const T dm = size_i + q.size; c = d2 < Rs2 || d2 < dm * dm * (T)1.000001; }
+            if (c) m8 |= 1u << k;
           }
           cand |= m8 << g0;
         }
