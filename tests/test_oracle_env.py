@@ -107,3 +107,47 @@ def test_threads_give_identical_results():
     for k in outs[0][0]:
         assert (outs[0][0][k] == outs[1][0][k]).all()
     assert (outs[0][1] == outs[1][1]).all()
+
+
+def test_closed_form_ballistic_motion_and_clamp():
+    """SPEC §2/§4 without contacts: v' = v(1-damping) + accel*u/mass*dt (then clamped), p' = p + v'dt."""
+    cfg = make_cfg("navigation", 3, "f64", n_obstacles=0, max_speed=[0.0, 0.5, 0.0])
+    e = O.OracleEnv(cfg, 1)
+    ag = np.array([[[-3.0, 0.0, 0.2, -0.1], [0.0, 3.0, 0.0, 0.0], [3.0, -3.0, -0.4, 0.3]]])
+    lm = np.array([[[5.0, 5.0], [6.0, 6.0], [7.0, 7.0]]])
+    e.set_state(ag, lm, [0])
+    u = np.array(cfg.discrete_u)
+    acts = np.array([[1, 3, 4]])
+    e.step(acts)
+    for i in range(3):
+        v = ag[0, i, 2:] * (1 - cfg.damping) + (cfg.accel[i] * u[acts[0, i]] / cfg.mass[i]) * cfg.dt
+        ms = cfg.max_speed[i]
+        if ms > 0 and np.hypot(*v) > ms:
+            v = v / np.hypot(*v) * ms
+        np.testing.assert_allclose(e.agent_state[0, i, 2:], v, rtol=1e-15, atol=1e-18)
+        np.testing.assert_allclose(e.agent_state[0, i, :2], ag[0, i, :2] + v * cfg.dt, rtol=1e-15, atol=1e-18)
+    assert np.isclose(np.hypot(*e.agent_state[0, 1, 2:]), 0.5)       # agent 1 hit its speed clamp
+    assert e.step_count[0] == 1
+
+
+def test_contact_forces_are_equal_and_opposite_and_match_softplus():
+    """SPEC §3: two overlapping agents, no action: the impulses are exactly opposite and equal to
+    contact_force * softplus(-(d - dmin)/margin) * margin along the line of centres."""
+    cfg = make_cfg("navigation", 2, "f64", n_obstacles=0)
+    e = O.OracleEnv(cfg, 1)
+    d = 0.15                                                          # dmin = 0.20 -> 0.05 overlap
+    ag = np.array([[[0.0, 0.0, 0.0, 0.0], [d * 0.6, d * 0.8, 0.0, 0.0]]])
+    lm = np.array([[[9.0, 9.0], [9.0, -9.0]]])
+    e.set_state(ag, lm, [0])
+    out = e.step(np.array([[0, 0]]))
+    v0, v1 = e.agent_state[0, 0, 2:], e.agent_state[0, 1, 2:]
+    assert (v0 == -v1).all()                                         # bit-exact action = reaction
+    k = cfg.contact_margin
+    pen = np.logaddexp(0.0, -(d - 0.2) / k) * k
+    f = cfg.contact_force * pen                                       # magnitude
+    np.testing.assert_allclose(np.hypot(*v1), f / cfg.mass[1] * cfg.dt, rtol=1e-12)
+    np.testing.assert_allclose(v1 / np.hypot(*v1), [0.6, 0.8], rtol=1e-12)
+    # the pair separated by exactly cf*dt^2/m * pen along the axis; cost counted before? no: after
+    assert out["cost"].tolist() == [[1.0, 1.0]] or out["cost"].tolist() == [[0.0, 0.0]]
+    new_d = np.hypot(*(e.agent_state[0, 1, :2] - e.agent_state[0, 0, :2]))
+    assert (new_d < 0.2) == bool(out["cost"][0, 0])                  # cost is taken on the post-step state
