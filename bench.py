@@ -348,7 +348,18 @@ def run_gpu(args):
     ms = ev0.elapsed_time(ev1)
     launches = env.kernel_launches - l0
     n_resets = K // EPISODE_LEN
-    clocks = sampler.stop(wall0, wall1)
+    if not any(wall0 <= ts <= wall1 for ts, _ in sampler.lines):
+        # the timed region was shorter than nvidia-smi's sampling period: keep the same kernel
+        # running (untimed) until a few samples exist, and say so in the record
+        wall0 = time.time()
+        while time.time() - wall0 < 0.6:
+            run_steps(T)
+            torch.cuda.synchronize()
+        wall1 = time.time()
+        clocks = sampler.stop(wall0, wall1)
+        clocks["window"] = "0.6 s of the same rollouts right after the timed region (region < sampling period)"
+    else:
+        clocks = sampler.stop(wall0, wall1)
 
     # dominant kernel alone, back to back on the same stream, CUDA events: the variant of the timed
     # region (compiled-in auto-reset, MODE 2) and the plain one (MODE 0)
