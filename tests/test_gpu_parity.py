@@ -737,3 +737,29 @@ def test_graph_vec_env_host_auto_reset():
     ag, lm, tt = vec.get_state()
     assert (tt == 0).all() and (ag == o.agent_state).all()
     vec.close()
+
+
+@pytest.mark.parametrize("name,N,B", [("navigation", 3, 8192), ("navigation", 12, 2048), ("polygon", 6, 4096)])
+def test_fp32_production_mode_is_statistically_equal_to_fp64(name, N, B):
+    """200 random-action steps with in-kernel auto-reset: individual fp32 trajectories drift from
+    the fp64 ones after contacts (stiff springs), but the rollout statistics a learner sees must
+    not: mean reward, mean cost, mean neighbour count, done count."""
+    T, E = 200, 25
+    stats = {}
+    for dtype in ("f64", "f32"):
+        cfg = make_cfg(name, N, dtype, episode_length=E)
+        env = _env(cfg, B, seed=11)
+        env.reset()
+        g = torch.Generator(device="cuda"); g.manual_seed(5)
+        acts = torch.randint(0, 5, (T, B, N), generator=g, device="cuda", dtype=torch.int32)
+        roll = env.rollout(acts, auto_reset=True)
+        stats[dtype] = dict(reward=roll["reward"].double().mean().item(), cost=roll["cost"].double().mean().item(),
+                            cnt=roll["nbr_cnt"].double().mean().item(), done=int(roll["done"].sum().item()),
+                            first_obs=roll["obs"][0].double().cpu().numpy())
+        env.close()
+    a, b = stats["f64"], stats["f32"]
+    np.testing.assert_allclose(b["first_obs"], a["first_obs"], rtol=1e-4, atol=1e-5)   # same start, one step
+    assert a["done"] == b["done"] == (T // E) * B * N
+    assert abs(a["reward"] - b["reward"]) < 2e-3 * abs(a["reward"]), (a["reward"], b["reward"])
+    assert abs(a["cnt"] - b["cnt"]) < 2e-3 * a["cnt"], (a["cnt"], b["cnt"])
+    assert a["cost"] > 0 and abs(a["cost"] - b["cost"]) < 0.03 * a["cost"], (a["cost"], b["cost"])
