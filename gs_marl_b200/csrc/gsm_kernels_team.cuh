@@ -30,10 +30,14 @@ __device__ __forceinline__ T sel(const T (&arr)[A], int idx) {
 // and columns per lane (row / column j belongs to lane j / A of the group, local index j % A).
 // Every lane of the warp calls it; groups are aligned runs of G lanes starting at `base`.
 // Returns col4row of the lane's A rows in c4r[].  Loops are bounded by N (no hang on NaN).
-template <typename T, int N, int G>
-__device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int base, bool live,
+// G lanes of a physical group of GP >= G lanes (GP a power of two) own the columns; lanes
+// g >= G of the group only take part in the warp primitives.  grp_live: the group holds a
+// problem; live = grp_live && g < G: this lane owns A rows / columns.
+template <typename T, int N, int G, int GP>
+__device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int base, bool grp_live,
                                           int (&c4r)[N / G]) {
   constexpr int A = N / G;
+  const bool live = grp_live && g < G;
   constexpr unsigned FULL = 0xffffffffu;
   const T INF = r_inf<T>();
   T u[A], v[A], spc[A];
@@ -44,14 +48,14 @@ __device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int ba
   for (int a = 0; a < A; a++) { u[a] = 0; v[a] = 0; path[a] = -1; r4c[a] = -1; c4r[a] = -1; spc[a] = INF; pos[a] = 0; inr[a] = false; }
   for (int cur = 0; cur < N; cur++) {
     T minval = 0;
-    int i = cur, nrem = N, sink = live ? -1 : 0;
+    int i = cur, nrem = N, sink = grp_live ? -1 : 0;
     unsigned sr = 0, sc = 0;
 #pragma unroll
     for (int a = 0; a < A; a++) { spc[a] = INF; pos[a] = N - 1 - (g * A + a); inr[a] = live; }
     for (int iter = 0; iter < N && __any_sync(FULL, sink == -1); iter++) {
       const bool run = sink == -1;
       const int ig = i / A, il = i - ig * A;
-      if (run && ig == g) sr |= 1u << il;
+      if (run && live && ig == g) sr |= 1u << il;
       const T u_i = shfl(FULL, sel<T, A>(u, il), base + ig);
       const T* Ci = Cg + i * N;
       T lo = INF;
@@ -65,7 +69,7 @@ __device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int ba
         lo = cand < lo ? cand : lo;
       }
 #pragma unroll
-      for (int m = G / 2; m >= 1; m >>= 1) {
+      for (int m = GP / 2; m >= 1; m >>= 1) {
         const T o = __shfl_xor_sync(FULL, lo, m);
         lo = o < lo ? o : lo;
       }
@@ -79,7 +83,7 @@ __device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int ba
         best = packed > best ? packed : best;
       }
 #pragma unroll
-      for (int m = G / 2; m >= 1; m >>= 1) {
+      for (int m = GP / 2; m >= 1; m >>= 1) {
         const int o = __shfl_xor_sync(FULL, best, m);
         best = o > best ? o : best;
       }
@@ -93,7 +97,7 @@ __device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int ba
         nrem--;
 #pragma unroll
         for (int a = 0; a < A; a++) {
-          if (jg == g && jl == a) { sc |= 1u << a; inr[a] = false; }
+          if (live && jg == g && jl == a) { sc |= 1u << a; inr[a] = false; }
           if (inr[a] && pos[a] == nrem) pos[a] = selpos;
         }
       }
@@ -119,7 +123,7 @@ __device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int ba
       if ((sc >> a) & 1u) v[a] -= minval - spc[a];
     // augment along the path
     int j = sink < 0 ? 0 : sink;
-    bool going = live && sink >= 0;
+    bool going = grp_live && sink >= 0;
     for (int iter = 0; iter < N && __any_sync(FULL, going); iter++) {
       const int jg = j / A, jl = j - jg * A;
       int arow = shfl(FULL, sel<int, A>(path, jl), base + jg);
@@ -146,22 +150,25 @@ __host__ __device__ inline size_t team_env_bytes(int rb, int N) {
   return ((size_t)(4 * N + N * N + N) * rb + 15) / 16 * 16;
 }
 
-template <typename T, int SCN, int N, int G>
+template <typename T, int SCN, int N, int G, int GP>
 __global__ void __launch_bounds__(kTeamThreads)
 env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
                 const __grid_constant__ StepStrides ss) {
-  constexpr int A = N / G, EPW = 32 / G, L = SCN == GSM_SCN_POLYGON ? 1 : 2, E = N + L;
-  static_assert(N % G == 0 && (G & (G - 1)) == 0 && G <= 32, "G lanes per env, A agents per lane");
+  constexpr int A = N / G, EPW = 32 / GP, L = SCN == GSM_SCN_POLYGON ? 1 : 2, E = N + L;
+  static_assert(N % G == 0 && (GP & (GP - 1)) == 0 && G <= GP && GP <= 32, "G of GP lanes per env, A agents per lane");
   static_assert(E <= 32, "adjacency is one 32-bit word");
   typedef Arith<T> AR;
   extern __shared__ __align__(128) unsigned char sm[];
   const int K = p.K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane % G, grp = lane / G, base = grp * G;
+  const int g = lane % GP, grp = lane / GP, base = grp * GP;
+  const bool has = g < G;                                 // this lane owns A agents / columns
   const int64_t env_w0 = ((int64_t)blockIdx.x * (kTeamThreads / 32) + warp) * EPW;   // first env of the warp
   const int64_t env_raw = env_w0 + grp;
-  const bool live = env_raw < p.n_envs;
-  const int64_t env = live ? env_raw : 0;                 // shadow groups compute, never store
+  const bool env_ok = env_raw < p.n_envs;
+  const bool live = env_ok && has;                        // lanes that store
+  const int64_t env = env_ok ? env_raw : 0;               // shadow groups compute, never store
+  const int ga = has ? g : 0;                             // idle lanes shadow lane 0's agents (no stores, no table writes)
 
   const size_t eb = team_env_bytes((int)sizeof(T), N);
   T* e_sm = (T*)(sm + (size_t)(warp * EPW + grp) * eb);
@@ -175,12 +182,12 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   bool coll_a[A];
 #pragma unroll
   for (int a = 0; a < A; a++) {
-    const int i = g * A + a;
+    const int i = ga * A + a;
     const T* s = p.agent_state + (env * N + i) * 4;
     px[a] = s[0]; py[a] = s[1]; vx[a] = s[2]; vy[a] = s[3];
     size_a[a] = p.size[i]; coll_a[a] = p.eflag[i] & 1;
     mass_a[a] = p.mass[i]; accel_a[a] = p.accel[i]; maxsp_a[a] = p.max_speed[i];
-    apos[2 * i] = px[a]; apos[2 * i + 1] = py[a]; avel[2 * i] = vx[a]; avel[2 * i + 1] = vy[a];
+    if (has) { apos[2 * i] = px[a]; apos[2 * i + 1] = py[a]; avel[2 * i] = vx[a]; avel[2 * i + 1] = vy[a]; }
   }
   T mx[L], my[L], msize[L];
   int mflag[L];
@@ -212,7 +219,7 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     // ---- SPEC §2-4 for my A agents (position table = state at the start of the step) ----------
 #pragma unroll
     for (int a = 0; a < A; a++) {
-      const int i = g * A + a;
+      const int i = ga * A + a;
       const int64_t row = env * N + i;
       T ux = 0, uy = 0;
       if (p.action_mode == GSM_ACT_DISCRETE) {
@@ -254,8 +261,8 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     __syncwarp();                                          // every lane has read the old table
 #pragma unroll
     for (int a = 0; a < A; a++) {
-      const int i = g * A + a;
-      apos[2 * i] = px[a]; apos[2 * i + 1] = py[a]; avel[2 * i] = vx[a]; avel[2 * i + 1] = vy[a];
+      const int i = ga * A + a;
+      if (has) { apos[2 * i] = px[a]; apos[2 * i + 1] = py[a]; avel[2 * i] = vx[a]; avel[2 * i + 1] = vy[a]; }
     }
     __syncwarp();
 
@@ -263,7 +270,7 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     T sx[A], sy[A];
 #pragma unroll
     for (int a = 0; a < A; a++) {
-      const int k = g * A + a;
+      const int k = ga * A + a;
       if (SCN == GSM_SCN_POLYGON) {
         sx[a] = mx[0] + p.poly_r * p.slot_table[2 * k];
         sy[a] = my[0] + p.poly_r * p.slot_table[2 * k + 1];
@@ -272,14 +279,14 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         sx[a] = mx[0] + f * (mx[L - 1] - mx[0]);
         sy[a] = my[0] + f * (my[L - 1] - my[0]);
       }
-      for (int r = 0; r < N; r++) {
+      for (int r = 0; r < N && has; r++) {
         const T dx = sx[a] - apos[2 * r], dy = sy[a] - apos[2 * r + 1];
         cmat[r * N + k] = r_sqrt(dx * dx + dy * dy);
       }
     }
     __syncwarp();
     int c4r[A];
-    lsa_group<T, N, G>(cmat, g, base, true, c4r);
+    lsa_group<T, N, G, GP>(cmat, g, base, true, c4r);
     __syncwarp();
 
     // ---- padding first: the rows of this warp's envs are one contiguous region -------------------
@@ -308,7 +315,7 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     T rew[A];
 #pragma unroll
     for (int a = 0; a < A; a++) {
-      const int i = g * A + a;
+      const int i = ga * A + a;
       const int64_t row = env * N + i;
       int cnt = 0, ncol = 0;
       uint32_t word = 0;
@@ -360,14 +367,14 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     }
     if (p.share_reward) {                                  // mean over the env's agents, ascending order
 #pragma unroll
-      for (int a = 0; a < A; a++) rsm[g * A + a] = rew[a];
+      for (int a = 0; a < A; a++) if (has) rsm[ga * A + a] = rew[a];
       __syncwarp();
       T s = rsm[0];
       for (int k = 1; k < N; k++) s = s + rsm[k];
       s = s / (T)N;
       if (live) {
 #pragma unroll
-        for (int a = 0; a < A; a++) ((T*)c_rew)[env * N + g * A + a] = s;
+        for (int a = 0; a < A; a++) ((T*)c_rew)[env * N + ga * A + a] = s;
       }
       __syncwarp();
     }
@@ -376,7 +383,7 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     if (auto_reset && t_now >= p.episode_length) {
 #pragma unroll
       for (int a = 0; a < A; a++) {
-        spawn_draw<T>(genv, ep, g * A + a, p.seed, p.ext[GSM_ENT_AGENT], px[a], py[a]);
+        spawn_draw<T>(genv, ep, ga * A + a, p.seed, p.ext[GSM_ENT_AGENT], px[a], py[a]);
         vx[a] = 0; vy[a] = 0;
       }
 #pragma unroll
@@ -388,8 +395,8 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       __syncwarp();
 #pragma unroll
       for (int a = 0; a < A; a++) {
-        const int i = g * A + a;
-        apos[2 * i] = px[a]; apos[2 * i + 1] = py[a]; avel[2 * i] = vx[a]; avel[2 * i + 1] = vy[a];
+        const int i = ga * A + a;
+        if (has) { apos[2 * i] = px[a]; apos[2 * i + 1] = py[a]; avel[2 * i] = vx[a]; avel[2 * i + 1] = vy[a]; }
       }
       __syncwarp();
     }
@@ -400,7 +407,7 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   if (live) {
 #pragma unroll
     for (int a = 0; a < A; a++) {
-      T* s = p.agent_state + (env * N + g * A + a) * 4;
+      T* s = p.agent_state + (env * N + ga * A + a) * 4;
       st2<T>(s, px[a], py[a]); st2<T>(s + 2, vx[a], vy[a]);
     }
     if (g == 0) {

@@ -262,29 +262,33 @@ int GSM_SFX(launch_lane)(const HostParams& hp, const gsm_step_io& io, int n_step
 }
 
 // ---- polygon / line kernel with the group-parallel assignment (gsm_kernels_team.cuh) -----------
-// (scenario, N, G): G lanes per env, N / G agents = assignment rows/columns per lane.
+// (scenario, N, G, GP): G working lanes in a physical group of GP lanes per env, N / G agents =
+// assignment rows/columns per lane.  The first entry of an (scenario, N) is the default,
+// GSM_TEAM_G picks another compiled one.
 #define GSM_TEAM_TABLE(X)                                                                     \
-  X(GSM_SCN_POLYGON, 3, 1) X(GSM_SCN_POLYGON, 4, 2) X(GSM_SCN_POLYGON, 5, 1) X(GSM_SCN_POLYGON, 6, 2) \
-  X(GSM_SCN_POLYGON, 12, 4)                                                                   \
-  X(GSM_SCN_LINE, 3, 1) X(GSM_SCN_LINE, 4, 2) X(GSM_SCN_LINE, 5, 1) X(GSM_SCN_LINE, 6, 2)     \
-  X(GSM_SCN_LINE, 12, 4)
+  X(GSM_SCN_POLYGON, 3, 1, 1) X(GSM_SCN_POLYGON, 4, 2, 2) X(GSM_SCN_POLYGON, 5, 1, 1)           \
+  X(GSM_SCN_POLYGON, 6, 3, 4) X(GSM_SCN_POLYGON, 6, 2, 2) X(GSM_SCN_POLYGON, 12, 4, 4)          \
+  X(GSM_SCN_LINE, 3, 1, 1) X(GSM_SCN_LINE, 4, 2, 2) X(GSM_SCN_LINE, 5, 1, 1)                    \
+  X(GSM_SCN_LINE, 6, 3, 4) X(GSM_SCN_LINE, 6, 2, 2) X(GSM_SCN_LINE, 12, 4, 4)
+// measured on B200 (profiles/README.md): N = 12: G=4 70 us, G=6 of 8 lanes 117 us, G=12 of 16 lanes
+// 94 us per step; N = 6: G=3 of 4 lanes 19.6 us, G=2 20.6 us, G=6 of 8 lanes 23.8 us.
 
 static bool has_team(const HostParams& hp) {
   if (env_int("GSM_NO_TEAM", 0) != 0 || env_int("GSM_NO_SPEC", 0) != 0 || env_int("GSM_FORCE_P", 0) != 0 ||
       env_int("GSM_FORCE_CTA_ENV", -1) >= 0 || env_int("GSM_SPEC_P", 0) != 0)
     return false;
-#define X(S, n, gg) if (hp.scenario == S && hp.N == n) return true;
+#define X(S, n, gg, gp) if (hp.scenario == S && hp.N == n) return true;
   GSM_TEAM_TABLE(X)
 #undef X
   return false;
 }
 
-template <int SCN, int N, int G>
+template <int SCN, int N, int G, int GP>
 static int launch_team_one(const KParams<GSM_REAL>& kp, int n_steps, const StepStrides& ss, cudaStream_t st) {
-  constexpr int EPW = 32 / G, WPC = kTeamThreads / 32;
+  constexpr int EPW = 32 / GP, WPC = kTeamThreads / 32;
   const int64_t grid = (kp.n_envs + EPW * WPC - 1) / (EPW * WPC);
   const size_t smem = (size_t)WPC * EPW * team_env_bytes((int)sizeof(GSM_REAL), N);
-  auto k = env_team_kernel<GSM_REAL, SCN, N, G>;
+  auto k = env_team_kernel<GSM_REAL, SCN, N, G, GP>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -303,7 +307,11 @@ int GSM_SFX(launch_team)(const HostParams& hp, const gsm_step_io& io, int n_step
   ss.actions = rs.actions; ss.obs = rs.obs; ss.nbr_idx = rs.nbr_idx; ss.nbr_feat = rs.nbr_feat;
   ss.nbr_cnt = rs.nbr_cnt; ss.adj = rs.adj; ss.reward = rs.reward; ss.cost = rs.cost;
   ss.done = rs.done; ss.assign = rs.assign;
-#define X(S, n, gg) if (hp.scenario == S && hp.N == n) return launch_team_one<S, n, gg>(kp, n_steps, ss, st);
+  const int want = env_int("GSM_TEAM_G", 0);
+#define X(S, n, gg, gp) if (hp.scenario == S && hp.N == n && want == gg) return launch_team_one<S, n, gg, gp>(kp, n_steps, ss, st);
+  GSM_TEAM_TABLE(X)
+#undef X
+#define X(S, n, gg, gp) if (hp.scenario == S && hp.N == n) return launch_team_one<S, n, gg, gp>(kp, n_steps, ss, st);
   GSM_TEAM_TABLE(X)
 #undef X
   return -1;
