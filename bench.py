@@ -320,33 +320,60 @@ def run_gpu(args):
     ring_bytes = sum(v.numel() * v.element_size() for v in ring.values())
 
     import ctypes as C
+    from gs_marl_b200.environment import StreamShardedEnv
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     io_full = env._make_io(ring, acts)                    # slot 0 of the [T][...] rollout buffers
     env._check(env.lib.gsm_set_auto_reset(env._h, 1))
+    # The timed region drives S contiguous sub-shards of this GPU's envs, each its own handle on
+    # its own stream, all filling the SAME rollout buffer (gsm_set_slot_envs): the tail of one
+    # shard's launch overlaps the body of the next (StreamShardedEnv docstring; --streams 1 = one handle).
+    S = max(1, args.streams)
+    sh_env = StreamShardedEnv(cfg, args.envs, n_streams=S, device=local, env_offset=rank * args.envs, seed=1)
+    sh_env.reset()
+    sh_io = [sh._make_io({k: ring[k][0, lo:hi] for k in env.OUTPUTS}, acts[0, lo:hi])
+             for sh, (lo, hi) in zip(sh_env.shards, sh_env.bounds)]
+    sh_streams = [C.c_void_p(st.cuda_stream) for st in sh_env.streams]
+    lib = env.lib
+
+    def set_auto(flag):
+        for sh in sh_env.shards:
+            sh._check(lib.gsm_set_auto_reset(sh._h, int(flag)))
 
     def run_steps(n):
-        """n env steps through the C ABI: fused rollouts of T steps (gsm_rollout); envs finish an
-        episode every EPISODE_LEN steps and are re-drawn inside the kernel, no other launch."""
+        """n env steps through the C ABI: fused rollouts of T steps (gsm_rollout), one launch per
+        sub-shard per T steps, round-robin over the shard streams, nothing joined in between; envs
+        finish an episode every EPISODE_LEN steps and are re-drawn inside the kernel."""
         done = 0
         while done < n:
             m = min(T, n - done)
-            env._check(env.lib.gsm_rollout(env._h, m, C.byref(io_full), stream))
+            for sh, io, st in zip(sh_env.shards, sh_io, sh_streams):
+                sh._check(lib.gsm_rollout(sh._h, m, C.byref(io), st))
             done += m
 
+    def timed(fn):
+        """CUDA events on the current stream around work enqueued on the shard streams: every
+        shard stream waits for the start event, the current stream waits for every shard stream."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for st in sh_env.streams:
+            st.wait_event(e0)
+        fn()
+        sh_env.join()
+        e1.record()
+        return e0, e1
+
+    set_auto(1)
     sampler = ClockSampler(local); sampler.start()
     run_steps(max(W, 3))
     barrier()
-    l0 = env.kernel_launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = sh_env.kernel_launches
     barrier()
     wall0 = time.time()
-    ev0.record()
-    run_steps(K)
-    ev1.record()
+    ev0, ev1 = timed(lambda: run_steps(K))
     barrier()
     wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
-    launches = env.kernel_launches - l0
+    launches = sh_env.kernel_launches - l0
     n_resets = K // EPISODE_LEN
     if not any(wall0 <= ts <= wall1 for ts, _ in sampler.lines):
         # the timed region was shorter than nvidia-smi's sampling period: keep the same kernel
@@ -361,13 +388,24 @@ def run_gpu(args):
     else:
         clocks = sampler.stop(wall0, wall1)
 
-    # dominant kernel alone, back to back on the same stream, CUDA events: the variant of the timed
-    # region (compiled-in auto-reset, MODE 2) and the plain one (MODE 0)
+    # dominant kernel, back to back, CUDA events: the variant of the timed region (compiled-in
+    # auto-reset, MODE 2) and the plain one (MODE 0); over the S shard streams (aggregate: all
+    # launches' bytes / elapsed) and as ONE launch over all envs on one stream
+    reps = max(2, min(40, K // T))
+
     def time_rollouts(auto):
+        set_auto(auto)
+        sh_env.reset()
+        run_steps(T)
+        torch.cuda.synchronize()
+        k0, k1 = timed(lambda: run_steps(reps * T))
+        torch.cuda.synchronize()
+        return k0.elapsed_time(k1) / (reps * T)
+
+    def time_rollouts_one_stream(auto):
         env.reset()
         env.rollout(acts, out=ring, auto_reset=auto)
         torch.cuda.synchronize()
-        reps = max(2, min(40, K // T))
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record()
         for _ in range(reps):
@@ -377,6 +415,9 @@ def run_gpu(args):
         return k0.elapsed_time(k1) / (reps * T)
     kern_ms = time_rollouts(True)
     kern_plain_ms = time_rollouts(False)
+    one_ms = time_rollouts_one_stream(True)
+    one_plain_ms = time_rollouts_one_stream(False)
+    set_auto(1)
     env._check(env.lib.gsm_set_auto_reset(env._h, 1))
 
     # ---- un-fused API: one gsm_step launch per env step (what a policy-in-the-loop caller uses) ----
@@ -473,7 +514,10 @@ def run_gpu(args):
                              "(> 126 MB L2); no explicit flush",
                 "episode": f"episode_length {EPISODE_LEN}: every env is re-drawn in-kernel {n_resets} times inside the "
                            "timed region (gsm_set_auto_reset)",
-                "launch": f"{T} fused steps per kernel launch (gsm_rollout)"}),
+                "launch": f"{T} fused steps per kernel launch (gsm_rollout); {S} contiguous env sub-shards of "
+                          f"{args.envs // S} envs, one handle + one CUDA stream each, one launch per shard per "
+                          f"{T} steps, all writing the same rollout buffer (gsm_set_slot_envs)",
+                "streams": S}),
             "env_steps_per_s": value / N_AGENTS,
             "clocks": clocks,
             "e2e": {"value": args.envs * N_AGENTS * Ke * world / (e2e_ms * 1e-3), "unit": UNIT,
@@ -485,7 +529,15 @@ def run_gpu(args):
                          "frac": achieved / peak, "traffic": ncu_traffic(),
                          "kernel": f"gsm::env_steps_kernel<float, NAVIGATION, 3, 6, P={spec_p}, MODE=2 (auto-reset)> "
                                    f"(one launch = {T} fused steps; achieved is per step)",
+                         "how": f"aggregate over {S} concurrent shard streams: algorithmic bytes of all launches of "
+                                "the region / CUDA-event time between a fork event every shard stream waits on and "
+                                "a join of all shard streams (same kernel, same envs, same buffer as `value`)",
                          "plain_variant_step_us": kern_plain_ms * 1e3,
+                         "one_stream": {"note": "the same envs as ONE launch per T steps on one stream (the state "
+                                                "before sub-shards; what a single ncu launch corresponds to)",
+                                        "step_us": one_ms * 1e3, "plain_variant_step_us": one_plain_ms * 1e3,
+                                        "achieved": bytes_launch / (one_ms * 1e-3) / 1e9,
+                                        "frac": bytes_launch / (one_ms * 1e-3) / 1e9 / peak},
                          "launch_us": kern_ms * 1e3 * T, "step_us": kern_ms * 1e3,
                          "algorithmic_bytes_per_launch": bytes_launch * T,
                          "algorithmic_bytes_per_step": bytes_launch,
@@ -519,6 +571,7 @@ def run_gpu(args):
 
         print(json.dumps(line), flush=True)
     env.close()
+    sh_env.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -596,6 +649,8 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--rollout-t", type=int, default=ROLLOUT_T, help="steps fused per launch")
+    ap.add_argument("--streams", type=int, default=4,
+                    help="env sub-shards per GPU, each on its own CUDA stream (1 = one handle, one stream)")
     ap.add_argument("--closed-loop-steps", type=int, default=1000)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--ref-budget", type=float, default=90.0)

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-GSM_ABI_VERSION = 4
+GSM_ABI_VERSION = 5
 GSM_OBS_DIM = 6
 GSM_NBR_FEAT_DIM = 6
 GSM_MAX_DISCRETE = 16
@@ -74,6 +74,7 @@ SYMBOLS = {
     "gsm_step": (C.c_int, [_H, _IO, C.c_void_p]),
     "gsm_rollout": (C.c_int, [_H, C.c_int32, _IO, C.c_void_p]),
     "gsm_set_auto_reset": (C.c_int, [_H, C.c_int]),
+    "gsm_set_slot_envs": (C.c_int, [_H, C.c_int64]),
     "gsm_observe": (C.c_int, [_H, _IO, C.c_void_p]),
     "gsm_set_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_get_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

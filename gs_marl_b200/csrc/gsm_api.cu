@@ -75,6 +75,7 @@ struct gsm_env {
   int64_t launches = 0;
   uint64_t seed = 0;
   int auto_reset = 0;      // gsm_set_auto_reset: applies inside gsm_rollout only
+  int64_t slot_envs = 0;   // gsm_set_slot_envs: envs per slot of the caller's [T][...] buffers (0: n_envs)
   std::string err;
 };
 
@@ -175,6 +176,13 @@ int do_env(gsm_env* h, const gsm_step_io& io, int physics, const uint8_t* mask, 
   return 0;
 }
 
+// Bytes between slot s and slot s+1 of rollout buffer k: the handle's own tensor size, or that of
+// a wider [T][slot_envs][...] buffer this handle's envs are a contiguous slice of.
+size_t slot_bytes(const gsm_env* h, int k) {
+  if (h->slot_envs <= 0 || h->hp.n_envs <= 0) return h->io_bytes[k];
+  return h->io_bytes[k] / (size_t)h->hp.n_envs * (size_t)h->slot_envs;
+}
+
 // One env step (physics + outputs): the size-specialised kernel when the handle has one.
 int do_steps(gsm_env* h, const gsm_step_io& io, int n_steps, cudaStream_t st, int observe = 0,
              const uint8_t* mask = nullptr, int64_t mask_stride = 0) {
@@ -183,11 +191,11 @@ int do_steps(gsm_env* h, const gsm_step_io& io, int n_steps, cudaStream_t st, in
   gsm::RolloutStrides rs;
   std::memset(&rs, 0, sizeof(rs));
   if (n_steps > 1) {
-    rs.actions = (int64_t)h->io_bytes[IO_ACTIONS]; rs.obs = (int64_t)h->io_bytes[IO_OBS];
-    rs.nbr_idx = (int64_t)h->io_bytes[IO_NBR_IDX]; rs.nbr_feat = (int64_t)h->io_bytes[IO_NBR_FEAT];
-    rs.nbr_cnt = (int64_t)h->io_bytes[IO_NBR_CNT]; rs.adj = (int64_t)h->io_bytes[IO_ADJ];
-    rs.reward = (int64_t)h->io_bytes[IO_REWARD]; rs.cost = (int64_t)h->io_bytes[IO_COST];
-    rs.done = (int64_t)h->io_bytes[IO_DONE]; rs.assign = (int64_t)h->io_bytes[IO_ASSIGN];
+    rs.actions = (int64_t)slot_bytes(h, IO_ACTIONS); rs.obs = (int64_t)slot_bytes(h, IO_OBS);
+    rs.nbr_idx = (int64_t)slot_bytes(h, IO_NBR_IDX); rs.nbr_feat = (int64_t)slot_bytes(h, IO_NBR_FEAT);
+    rs.nbr_cnt = (int64_t)slot_bytes(h, IO_NBR_CNT); rs.adj = (int64_t)slot_bytes(h, IO_ADJ);
+    rs.reward = (int64_t)slot_bytes(h, IO_REWARD); rs.cost = (int64_t)slot_bytes(h, IO_COST);
+    rs.done = (int64_t)slot_bytes(h, IO_DONE); rs.assign = (int64_t)slot_bytes(h, IO_ASSIGN);
   }
   int e = -1;
   if (h->plan.team && !observe)
@@ -438,6 +446,18 @@ int gsm_set_auto_reset(gsm_env* h, int enabled) {
   return GSM_OK;
 }
 
+int gsm_set_slot_envs(gsm_env* h, int64_t slot_envs) {
+  if (!h) return GSM_ERR_INVALID_ARG;
+  if (slot_envs != 0 && slot_envs < h->hp.n_envs)
+    return fail(h, GSM_ERR_INVALID_ARG, "slot_envs must be 0 or >= the handle's n_envs");
+  if (slot_envs != h->slot_envs && h->graph_exec) {     // cached graph has the other strides
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+  }
+  h->slot_envs = slot_envs;
+  return GSM_OK;
+}
+
 int gsm_rollout(gsm_env* h, int32_t n_steps, const gsm_step_io* io, void* stream) {
   if (!h || !io || n_steps < 1) return GSM_ERR_INVALID_ARG;
   if (!io->actions) return fail(h, GSM_ERR_INVALID_ARG, "io.actions is NULL");
@@ -462,7 +482,7 @@ int gsm_rollout(gsm_env* h, int32_t n_steps, const gsm_step_io* io, void* stream
       gsm_step_io cur;
       for (int k = 0; k < IO_COUNT; k++) {
         unsigned char* b = (unsigned char*)io_get(*io, k);
-        io_set(cur, k, b ? b + (size_t)s * h->io_bytes[k] : nullptr);
+        io_set(cur, k, b ? b + (size_t)s * slot_bytes(h, k) : nullptr);
       }
       st = do_step(h, cur, h->stream);
       if (st == 0 && h->auto_reset) {                  // masked re-draw of the envs that just finished

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GSM_ABI_VERSION 4
+#define GSM_ABI_VERSION 5
 
 #define GSM_OBS_DIM 6        /* vx, vy, px, py, target_dx, target_dy          (SPEC.md §6) */
 #define GSM_NBR_FEAT_DIM 6   /* dx, dy, dvx, dvy, dist, (real)entity_type     (SPEC.md §6) */
@@ -183,6 +183,15 @@ int gsm_rollout(gsm_env* h, int32_t n_steps, const gsm_step_io* io, void* stream
  * keeps its terminal outputs in slot s and is re-drawn (same Philox stream as gsm_reset with
  * the handle's current seed) before step s+1.  gsm_step is not affected. */
 int gsm_set_auto_reset(gsm_env* h, int enabled);
+
+/* Slot stride of gsm_rollout, in envs: the io pointers aim at this handle's first env inside
+ * [T][slot_envs][...] tensors that are wider than the handle (slot_envs >= n_envs; 0 restores
+ * the handle's own n_envs).  Lets several handles that each own a contiguous env range of one
+ * GPU — sub-shards on their own CUDA streams, so the tail of one fused rollout overlaps the body
+ * of another's — fill ONE rollout buffer (the buffer insert of utils/graph_separated_buffer.py,
+ * SOURCES.txt:33, stays a no-op).  gsm_step / gsm_reset are not affected: their tensors are one
+ * slot, and a contiguous env slice of it is already a valid io. */
+int gsm_set_slot_envs(gsm_env* h, int64_t slot_envs);
 
 /* _get_obs + graph build for the current state, no physics (environment.py). */
 int gsm_observe(gsm_env* h, const gsm_step_io* io, void* stream);

@@ -2,11 +2,13 @@
 
     python profiles/bench_configs.py [--dtype f32] [--json out.json] [--only substr]
 
-Prints one line per configuration: step time, agent-steps/s, algorithmic GB/s and the
-fraction of the measured HBM peak.  Uses gsm_rollout (fused launch where a specialised
-kernel exists, CUDA graph of generic steps otherwise) into a T-slot rollout buffer.
+Prints two lines per configuration — one handle on one stream, and `--streams` sub-shards on
+concurrent streams (StreamShardedEnv) — each with step time, agent-steps/s, algorithmic GB/s and
+the fraction of the measured HBM peak.  Uses gsm_rollout with in-kernel auto-reset (fused launch
+where a specialised kernel exists, CUDA graph of generic steps otherwise) into a T-slot buffer.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import sys
@@ -16,7 +18,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from gs_marl_b200 import scenarios  # noqa: E402
-from gs_marl_b200.environment import MultiAgentGraphConstrainEnv  # noqa: E402
+from gs_marl_b200.environment import MultiAgentGraphConstrainEnv, StreamShardedEnv  # noqa: E402
 
 CONFIGS = [  # (label, scenario, N, n_envs, kwargs)
     ("cfg1 nav-3 x16384", "navigation", 3, 16384, {}),
@@ -38,6 +40,7 @@ def main():
     ap.add_argument("--dtype", default="f32")
     ap.add_argument("--json", default=None)
     ap.add_argument("--only", default=None)
+    ap.add_argument("--streams", type=int, default=4, help="sub-shards on concurrent streams (second column)")
     args = ap.parse_args()
     peak = 6546.2
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -50,30 +53,51 @@ def main():
         cfg = scenarios.load(scn).make_world(N, dtype=args.dtype, **kw)
         bpas = cfg.bytes_per_agent_step()
         T = 8 if bpas * N * n_envs * 25 > 8e9 else 25
-        env = MultiAgentGraphConstrainEnv(cfg, n_envs, seed=3)
-        env.reset()
         acts = torch.randint(0, 5, (T, n_envs, N), device="cuda", dtype=torch.int32)
-        ring = {k: env._alloc(k, (T,)) for k in env.OUTPUTS}
-        env.rollout(acts, out=ring)
-        torch.cuda.synchronize()
-        reps = 5
-        l0 = env.kernel_launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            env.rollout(acts, out=ring)
-        e1.record()
-        torch.cuda.synchronize()
-        step_us = e0.elapsed_time(e1) * 1e3 / (reps * T)
-        gbs = bpas * N * n_envs / (step_us * 1e-6) / 1e9
-        rec = {"config": label, "dtype": args.dtype, "step_us": step_us,
-               "agent_steps_per_s": N * n_envs / (step_us * 1e-6), "bytes_per_agent_step": bpas,
-               "achieved_gbs": gbs, "frac_of_measured_hbm": gbs / peak,
-               "launches_per_rollout": (env.kernel_launches - l0) // reps, "steps_per_rollout": T}
+        ring = None
+        rec = {"config": label, "dtype": args.dtype, "bytes_per_agent_step": bpas, "steps_per_rollout": T}
+        # both columns run the steady state of the bench: auto-reset on, episode_length of the preset
+        for col, S in (("one_stream", 1), (f"streams_{args.streams}", args.streams)):
+            env = (MultiAgentGraphConstrainEnv(cfg, n_envs, seed=3) if S == 1 else
+                   StreamShardedEnv(cfg, n_envs, n_streams=S, seed=3))
+            env.reset()
+            if ring is None:
+                ring = {k: env._alloc(k, (T,)) for k in env.OUTPUTS}
+            if S == 1:
+                io = env._make_io(ring, acts)
+                env._check(env.lib.gsm_set_auto_reset(env._h, 1))
+                st = env._stream()
+
+                def launch(env=env, io=io, st=st):
+                    env._check(env.lib.gsm_rollout(env._h, T, C.byref(io), st))
+                join = lambda: None
+            else:
+                launch, join = env.rollout_plan(acts, ring, auto_reset=True), env.join
+            for _ in range(4):
+                launch()
+            join()
+            torch.cuda.synchronize()
+            reps = 8
+            l0 = env.kernel_launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if S > 1:
+                for s_ in env.streams:
+                    s_.wait_event(e0)
+            for _ in range(reps):
+                launch()
+            join()
+            e1.record()
+            torch.cuda.synchronize()
+            step_us = e0.elapsed_time(e1) * 1e3 / (reps * T)
+            gbs = bpas * N * n_envs / (step_us * 1e-6) / 1e9
+            rec[col] = {"step_us": step_us, "agent_steps_per_s": N * n_envs / (step_us * 1e-6),
+                        "achieved_gbs": gbs, "frac_of_measured_hbm": gbs / peak,
+                        "launches_per_rollout": (env.kernel_launches - l0) // reps}
+            print(f"{label:36s} {col:11s} {step_us:9.2f} us/step  {rec[col]['agent_steps_per_s']:.3e} agent-steps/s  "
+                  f"{gbs:7.1f} GB/s  {gbs / peak:6.1%}  launches/rollout={rec[col]['launches_per_rollout']}", flush=True)
+            env.close()
         out.append(rec)
-        print(f"{label:36s} {step_us:9.2f} us/step  {rec['agent_steps_per_s']:.3e} agent-steps/s  "
-              f"{gbs:7.1f} GB/s  {gbs / peak:6.1%}  launches/rollout={rec['launches_per_rollout']}", flush=True)
-        env.close()
         del ring, acts
         torch.cuda.empty_cache()
     if args.json:

@@ -768,3 +768,72 @@ def test_fp32_production_mode_is_statistically_equal_to_fp64(name, N, B):
     assert abs(a["reward"] - b["reward"]) < 2e-3 * abs(a["reward"]), (a["reward"], b["reward"])
     assert abs(a["cnt"] - b["cnt"]) < 2e-3 * a["cnt"], (a["cnt"], b["cnt"])
     assert a["cost"] > 0 and abs(a["cost"] - b["cost"]) < 0.03 * a["cost"], (a["cost"], b["cost"])
+
+
+# ---- intra-GPU sub-shards on concurrent streams -----------------------------------------------
+@pytest.mark.parametrize("name,N,kw,env_vars", [
+    ("navigation", 3, {}, {}),                                   # specialised kernel
+    ("navigation", 12, {}, {}),                                  # lane kernel
+    ("polygon", 6, {}, {}),                                      # team kernel
+    ("navigation", 33, {"n_obstacles": 0, "max_nbrs": 65}, {"GSM_NO_LANE": "1"}),   # generic -> CUDA-graph rollout
+])
+@pytest.mark.parametrize("dtype,S", [("f64", 3), ("f32", 4)])
+def test_stream_sharded_env_is_bit_identical_to_one_handle(name, N, kw, env_vars, dtype, S, monkeypatch):
+    """StreamShardedEnv (S handles on S streams filling ONE set of [T][n_envs] buffers through
+    gsm_set_slot_envs) == one handle over the same envs, bit for bit: reset, masked reset, step,
+    fused rollouts with in-kernel auto-reset, back-to-back un-joined rollouts, final state.  The
+    fp64 leg is also checked against the oracle."""
+    from gs_marl_b200.environment import StreamShardedEnv
+    for k, v in env_vars.items():
+        monkeypatch.setenv(k, v)
+    cfg = make_cfg(name, N, dtype, episode_length=5, **kw)
+    B, T, seed = 29, 7, 5                                        # ragged: 29 envs over 3 / 4 shards
+    one = _env(cfg, B, seed=seed, env_offset=100)
+    many = StreamShardedEnv(cfg, B, n_streams=S, seed=seed, env_offset=100)
+    assert [hi - lo for lo, hi in many.bounds] == sorted([hi - lo for lo, hi in many.bounds], reverse=True)
+    assert sum(hi - lo for lo, hi in many.bounds) == B
+
+    def same(a, b, ctx):
+        a, b = _np(a), _np(b)
+        for k in a:
+            if k in b:
+                assert np.array_equal(a[k], b[k], equal_nan=True), (ctx, k)
+
+    o1, g1 = one.reset()
+    o2, g2 = many.reset()
+    same(dict(obs=o1, **g1), dict(obs=o2, **g2), "reset")
+    rng = np.random.default_rng(3)
+    acts = random_actions(cfg, rng, (3 * T, B))
+    r1 = one.step(acts[0]); r2 = many.step(acts[0])
+    first_step = _np(dict(obs=r2[0], reward=r2[2], cost=r2[3], done=r2[4], assign=r2[5]["assign"], **r2[1]))
+    same(dict(obs=r1[0], reward=r1[2], cost=r1[3], done=r1[4], **r1[1]), first_step, "step")
+    mask = torch.tensor((np.arange(B) % 3 == 0).astype(np.uint8), device="cuda")
+    o1, g1 = one.reset(mask); o2, g2 = many.reset(mask)
+    same(dict(obs=o1, **g1), dict(obs=o2, **g2), "masked reset")
+    # three back-to-back rollouts, the sharded ones left un-joined until the end
+    outs1 = [one.rollout(acts[q * T:(q + 1) * T], auto_reset=True) for q in range(3)]
+    outs2 = [many.rollout(acts[q * T:(q + 1) * T], auto_reset=True, join=False) for q in range(3)]
+    many.join()
+    torch.cuda.synchronize()
+    for q in range(3):
+        same(outs1[q], outs2[q], f"rollout {q}")
+    for a, b in zip(one.get_state(), many.get_state()):
+        assert torch.equal(a, b)
+    assert many.kernel_launches >= S
+    if dtype == "f64":
+        from oracle import gsm_oracle as O
+        o = O.OracleEnv(cfg, B, env_offset=100)
+        o.reset(seed)
+        w = {k: v.copy() for k, v in o.step(acts[0]).items()}
+        assert_match(first_step, w, rtol=F64_RTOL, atol=F64_ATOL, ctx="sharded step vs oracle")
+    one.close(); many.close()
+
+
+def test_slot_envs_argument_checks():
+    cfg = make_cfg("navigation", 3, "f32")
+    env = _env(cfg, 8)
+    assert env.lib.gsm_set_slot_envs(env._h, 4) == -1            # narrower than the handle
+    assert b"slot_envs" in env.lib.gsm_last_error(env._h)
+    assert env.lib.gsm_set_slot_envs(env._h, 8) == 0 and env.lib.gsm_set_slot_envs(env._h, 0) == 0
+    assert env.lib.gsm_set_slot_envs(None, 8) == -1
+    env.close()
