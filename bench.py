@@ -467,6 +467,7 @@ def run_gpu(args):
     closed = None
     if args.closed_loop_steps > 0:
         closed = closed_loop(env, cfg, args.closed_loop_steps, dev)
+        closed["fused_actor"] = closed_loop_fused(cfg, args.envs, args.closed_loop_steps, local, rank)
 
     # ---- e2e through the numpy-facing drop-in ------------------------------------------------
     vec = GraphVecEnv(cfg, args.envs, device=local, env_offset=rank * args.envs, seed=1)
@@ -567,6 +568,7 @@ def run_gpu(args):
             line["roofline_large_batch"] = large
         if closed is not None:
             closed["value"] *= world           # every rank runs the same closed loop on its shard
+            closed["fused_actor"]["value"] *= world
             line["closed_loop"] = closed
 
         print(json.dumps(line), flush=True)
@@ -574,6 +576,70 @@ def run_gpu(args):
     sh_env.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def closed_loop_fused(cfg, n_envs, n_steps, local, rank):
+    """Closed loop with THIS library's actor kernel and C-level collect loop (f1):
+    gsm_collect = per env step one graph_actor_kernel launch (forward + Gumbel-max sampling +
+    log-prob, weights in the kernel parameter space) and one env-step launch, written straight into
+    a [T+1]/[T] rollout buffer (f2); the 2T launches are replayed from a CUDA graph; the env is
+    reset between rollouts.  Same declared actor architecture as the torch policy above."""
+    import torch
+    from gs_marl_b200.environment import MultiAgentGraphConstrainEnv
+    from gs_marl_b200.policy import GraphAttentionActor
+    from gs_marl_b200.rollout import GraphRolloutBuffer, collect_fused
+    dev = torch.device("cuda", local)
+    env = MultiAgentGraphConstrainEnv(cfg, n_envs, device=local, env_offset=rank * n_envs, seed=3)
+    actor = GraphAttentionActor(len(cfg.discrete_u), seed=0)
+    T = EPISODE_LEN
+    buf = GraphRolloutBuffer(env, T)
+    buf.reset_env()
+    g = collect_fused(env, actor, buf, seed=1, first_step=0, graph=True)
+    for _ in range(2):
+        g.replay(); buf.reset_env()
+    torch.cuda.synchronize()
+    reps = max(1, n_steps // T)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+        buf.reset_env()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    # the actor kernel alone on one slot of the buffer
+    obs, graph = buf["obs"][1], buf.graph(1)
+    out = (buf["actions"][0], buf["logp"][0])
+    for _ in range(3):
+        actor.act(obs, graph, seed=1, step=0, out=out)
+    torch.cuda.synchronize()
+    ga = torch.cuda.CUDAGraph()            # 50 launches per replay: device time, not Python time
+    with torch.cuda.graph(ga):
+        for q in range(50):
+            actor.act(obs, graph, seed=1, step=q, out=out)
+    ga.replay()
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for q in range(4):
+        ga.replay()
+    k1.record()
+    torch.cuda.synchronize()
+    actor_us = k0.elapsed_time(k1) * 1e3 / 200
+    cnt = graph["nbr_cnt"].float()
+    rows = float(cnt.sum().item())
+    n_agents = cnt.numel()
+    H, A = 64, len(cfg.discrete_u)
+    flops = 2.0 * (n_agents * H * (6 + A) + rows * H * (6 + 1 + A))
+    env.close()
+    return {"value": n_envs * cfg.n_agents * reps * T / (ms * 1e-3), "unit": UNIT, "steps": reps * T,
+            "ms_per_step": ms / (reps * T),
+            "policy": "graph_actor_kernel<5> (this library, fp32, weights as kernel parameters) via gsm_collect; "
+                      f"CUDA graph of {2 * T} launches per {T}-step rollout + reset per rollout",
+            "actor_kernel_us": actor_us, "mean_valid_rows_per_agent": rows / n_agents,
+            "actor_tflops": flops / (actor_us * 1e-6) / 1e12,
+            "actor_bound": "fp32 issue (FFMA with uniform-register weight operands); "
+                           "B200 fp32 peak 148 SM x 128 FMA/clk x 2 x 1.965 GHz = 74.5 TFLOP/s"}
 
 
 def closed_loop(env, cfg, n_steps, dev):

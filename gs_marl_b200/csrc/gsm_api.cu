@@ -603,6 +603,46 @@ int gsm_get_state_host(gsm_env* h, void* agent_state, void* landmark_pos, int32_
   return GSM_OK;
 }
 
+int gsm_collect(gsm_env* h, const gsm_policy_weights* w, int32_t n_steps, const gsm_step_io* io,
+                float* logp, uint64_t seed, uint64_t first_step, int32_t greedy, void* stream) {
+  if (!h || !io || !w || n_steps < 1) return GSM_ERR_INVALID_ARG;
+  if (!is_f32(h) || h->hp.action_mode != GSM_ACT_DISCRETE)
+    return fail(h, GSM_ERR_UNSUPPORTED, "gsm_collect needs a GSM_F32 handle with discrete actions");
+  if (w->n_actions != h->hp.n_actions)
+    return fail(h, GSM_ERR_INVALID_ARG, "gsm_collect: weights.n_actions != cfg.n_discrete_actions");
+  if (!io->actions || !io->obs || !io->nbr_feat || !io->nbr_cnt)
+    return fail(h, GSM_ERR_INVALID_ARG, "gsm_collect needs io.actions, io.obs, io.nbr_feat and io.nbr_cnt");
+  DeviceGuard guard(h->device);
+  const int64_t rows = h->hp.n_envs * h->hp.N;
+  const int64_t slot_rows = (h->slot_envs ? h->slot_envs : h->hp.n_envs) * h->hp.N;
+  for (int t = 0; t < n_steps; t++) {
+    gsm_step_io cur;     // step outputs: slot t; observation outputs: slot t + 1
+    for (int k = 0; k < IO_COUNT; k++) {
+      unsigned char* b = (unsigned char*)io_get(*io, k);
+      const bool obs_like = k == IO_OBS || k == IO_NBR_IDX || k == IO_NBR_FEAT || k == IO_NBR_CNT ||
+                            k == IO_ADJ || k == IO_ASSIGN;
+      io_set(cur, k, b ? b + (size_t)(t + (obs_like ? 1 : 0)) * slot_bytes(h, k) : nullptr);
+    }
+    gsm_policy_io pio;
+    pio.obs = (const float*)((const unsigned char*)io->obs + (size_t)t * slot_bytes(h, IO_OBS));
+    pio.nbr_feat = (const float*)((const unsigned char*)io->nbr_feat + (size_t)t * slot_bytes(h, IO_NBR_FEAT));
+    pio.nbr_cnt = (const int32_t*)((const unsigned char*)io->nbr_cnt + (size_t)t * slot_bytes(h, IO_NBR_CNT));
+    pio.actions = (int32_t*)const_cast<void*>(cur.actions);
+    pio.logp = logp ? logp + (size_t)t * slot_rows : nullptr;
+    pio.logits = nullptr;
+    pio.n_rows = rows;
+    pio.row_offset = (uint64_t)h->hp.env_offset * (uint64_t)h->hp.N;
+    pio.seed = seed; pio.step = first_step + (uint64_t)t;
+    pio.max_nbrs = h->hp.K; pio.greedy = greedy;
+    int st = gsm_policy_act(w, &pio, h->device, stream);
+    if (st) return fail(h, st, gsm_policy_last_error());
+    h->launches += 1;
+    st = do_step(h, cur, (cudaStream_t)stream);
+    if (st) return st;
+  }
+  return GSM_OK;
+}
+
 int64_t gsm_kernel_launches(const gsm_env* h) { return h ? h->launches : 0; }
 
 int gsm_lsa(const void* cost, int32_t* col4row, int64_t n_problems, int32_t n, int32_t dtype,

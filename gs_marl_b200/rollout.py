@@ -35,7 +35,13 @@ class GraphRolloutBuffer:
         for k in _STEP_KEYS + ("actions",):
             dt, shape = sh[k]
             self.data[k] = torch.zeros((self.T,) + tuple(shape), dtype=_TORCH_DT[dt], device=dev)
+        self.data["logp"] = torch.zeros((self.T,) + tuple(sh["reward"][1]), dtype=torch.float32, device=dev)
         self.step = 0
+        # slot 0 of every tensor: what gsm_collect takes (it strides through the slots itself)
+        io_all = abi.GsmStepIO()
+        for k in _OBS_KEYS + _STEP_KEYS + ("actions",):
+            setattr(io_all, k, self.data[k].data_ptr())
+        self._io_all = io_all
         # one pre-built io struct per step: outputs of step t land in obs-slot t+1 / step-slot t
         self._io = []
         for t in range(self.T):
@@ -82,3 +88,36 @@ def collect(env: MultiAgentGraphConstrainEnv, policy: Callable, buf: GraphRollou
             env._check(env.lib.gsm_step(env._h, C.byref(buf._io[t]), stream))
     buf.step = buf.T
     return buf
+
+
+def collect_fused(env: MultiAgentGraphConstrainEnv, actor, buf: GraphRolloutBuffer, seed: int = 0,
+                  first_step: int = 0, greedy: bool = False, graph: bool = False):
+    """The same rollout with the actor forward + sampling as this library's kernel
+    (`gsm_collect`: per step one actor launch and one env-step launch, enqueued from C with no
+    Python or host sync in between; actions and log-probs land in the buffer slots).  `actor` is a
+    `policy.GraphAttentionActor`.  graph=True captures the 2·T launches into a CUDA graph and
+    returns it WITHOUT having advanced the env (replay runs the rollout from the env's current
+    state and whatever slot 0 holds, with the Philox step counters and the weights baked in at
+    capture: re-capture after an optimizer step)."""
+    w = actor.packed()
+
+    def enqueue(stream):
+        env._check(env.lib.gsm_collect(env._h, C.byref(w), buf.T, C.byref(buf._io_all),
+                                       C.c_void_p(buf.data["logp"].data_ptr()), int(seed), int(first_step),
+                                       int(bool(greedy)), stream))
+    with torch.cuda.device(env.device):
+        if not graph:
+            enqueue(env._stream())
+            buf.step = buf.T
+            return buf
+        # one eager rollout first (module load / first-launch work must not happen inside a
+        # capture); the env state is put back afterwards, slot 0 is never written by a collect
+        saved = env.get_state()
+        enqueue(env._stream())
+        env.set_state(*saved)
+        torch.cuda.synchronize(env.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            enqueue(env._stream())
+        buf.step = buf.T
+        return g

@@ -33,12 +33,14 @@
 extern "C" {
 #endif
 
-#define GSM_ABI_VERSION 5
+#define GSM_ABI_VERSION 6
 
 #define GSM_OBS_DIM 6        /* vx, vy, px, py, target_dx, target_dy          (SPEC.md §6) */
 #define GSM_NBR_FEAT_DIM 6   /* dx, dy, dvx, dvy, dist, (real)entity_type     (SPEC.md §6) */
 #define GSM_MAX_DISCRETE 16
 #define GSM_MAX_LSA_N 32     /* one warp lane per assignment column */
+#define GSM_POLICY_HIDDEN 64       /* hidden width of the declared graph actor (SPEC.md §9) */
+#define GSM_POLICY_MAX_ACTIONS 9   /* rows of head_w; compiled instances: n_actions 5 and 9  */
 
 typedef enum gsm_status {
   GSM_OK = 0,
@@ -230,6 +232,60 @@ int64_t gsm_kernel_launches(const gsm_env* h);
  * int32 [n_problems][n].  dtype: gsm_dtype.  1 <= n <= GSM_MAX_LSA_N. */
 int gsm_lsa(const void* cost, int32_t* col4row, int64_t n_problems, int32_t n,
             int32_t dtype, int device, void* stream);
+
+/* ---- SURVEY.md §8 "next" rows f3 + f1: actor forward over the padded graph, collect loop ------
+ * Reference side (withheld): the GNN actor of gsmarl/algorithms (torch-geometric,
+ * requirements.txt:119) evaluated once per env step by runner/mpe_runner.py's collect
+ * (SOURCES.txt:28), whose results go into utils/graph_separated_buffer.py (SOURCES.txt:33).
+ * The architecture is the DECLARED one of SPEC.md §9 (parameters shared by all agents):
+ *   e = relu(ego_w obs + ego_b); m_r = relu(nbr_w feat_r + nbr_b) for the nbr_cnt valid rows;
+ *   a = softmax_r(att_w . m_r + att_b); z = head_w [e ; sum_r a_r m_r] + head_b;
+ *   action = argmax_k(z_k - log(-log(u_k))), u from Philox4x32-10 with key = seed and counter
+ *   (row_offset + row, step, 0x80000000 | k/4) — or argmax_k z_k when greedy != 0.
+ * Weight matrices are row-major [out][in] like torch.nn.Linear.weight; HOST memory (they travel
+ * in the kernel's parameter space).  fp32 only. */
+typedef struct gsm_policy_weights {
+  uint32_t struct_size;          /* = sizeof(gsm_policy_weights); checked */
+  int32_t n_actions;             /* 5 or 9 */
+  float ego_w[GSM_POLICY_HIDDEN][GSM_OBS_DIM];
+  float ego_b[GSM_POLICY_HIDDEN];
+  float nbr_w[GSM_POLICY_HIDDEN][GSM_NBR_FEAT_DIM];
+  float nbr_b[GSM_POLICY_HIDDEN];
+  float att_w[GSM_POLICY_HIDDEN];
+  float att_b;
+  float head_w[GSM_POLICY_MAX_ACTIONS][2 * GSM_POLICY_HIDDEN];   /* rows >= n_actions ignored */
+  float head_b[GSM_POLICY_MAX_ACTIONS];
+} gsm_policy_weights;
+
+typedef struct gsm_policy_io {   /* DEVICE pointers; a "row" is one agent of one env */
+  const float* obs;        /* [n_rows][GSM_OBS_DIM]                     */
+  const float* nbr_feat;   /* [n_rows][max_nbrs][GSM_NBR_FEAT_DIM]      */
+  const int32_t* nbr_cnt;  /* [n_rows]  valid rows (clamped to [0, max_nbrs]) */
+  int32_t* actions;        /* [n_rows]  out                             */
+  float* logp;             /* [n_rows]  out, log pi(action); NULL = skip */
+  float* logits;           /* [n_rows][n_actions] out; NULL = skip       */
+  int64_t n_rows;
+  uint64_t row_offset;     /* global index of row 0 (env_offset * N): sharding-invariant draws */
+  uint64_t seed, step;
+  int32_t max_nbrs;
+  int32_t greedy;
+} gsm_policy_io;
+
+int gsm_policy_act(const gsm_policy_weights* w, const gsm_policy_io* io, int device, void* stream);
+const char* gsm_policy_last_error(void);
+
+/* n_steps of {actor forward + sampling, env step} enqueued on `stream` with no host sync (2
+ * kernels per step; capturable into a CUDA graph).  io->obs / nbr_* / adj / assign point at slot 0
+ * of [n_steps+1][...] tensors whose slot 0 already holds the current observation (gsm_reset,
+ * gsm_observe or the previous collect's last slot); io->actions / reward / cost / done point at
+ * slot 0 of [n_steps][...] tensors; logp: float [n_steps][n_envs][N] or NULL.  Step t: the actor
+ * reads observation slot t and writes actions (and logp) slot t with Philox step first_step + t;
+ * gsm_step writes reward / cost / done slot t and the next observation into slot t + 1 — the
+ * buffer "insert" is where the kernels write.  Slot strides follow gsm_get_io_sizes /
+ * gsm_set_slot_envs.  Needs a GSM_F32, GSM_ACT_DISCRETE handle with n_discrete_actions ==
+ * w->n_actions. */
+int gsm_collect(gsm_env* h, const gsm_policy_weights* w, int32_t n_steps, const gsm_step_io* io,
+                float* logp, uint64_t seed, uint64_t first_step, int32_t greedy, void* stream);
 
 #ifdef __cplusplus
 }
