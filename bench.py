@@ -488,6 +488,18 @@ def run_gpu(args):
     h2d = host_acts[0].nbytes
     d2h = sum(v.nbytes for k, v in vec.buf.items() if k != "actions")
     vec.close()
+    # the ceiling of that path on this box: one pinned D2H copy of the same size, nothing else
+    dsrc = torch.empty(d2h, dtype=torch.uint8, device=dev)
+    hdst = torch.empty(d2h, dtype=torch.uint8, pin_memory=True)
+    for _ in range(3):
+        hdst.copy_(dsrc, non_blocking=True)
+    torch.cuda.synchronize()
+    tp0 = time.perf_counter()
+    for _ in range(20):
+        hdst.copy_(dsrc, non_blocking=True)
+        torch.cuda.synchronize()
+    pcie_d2h_gbs = d2h * 20 / (time.perf_counter() - tp0) / 1e9
+    del dsrc, hdst
 
     tms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -524,7 +536,13 @@ def run_gpu(args):
             "e2e": {"value": args.envs * N_AGENTS * Ke * world / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "api": "GraphVecEnv.step -> gsm_step_host (pinned arena; 1 H2D + 1 kernel + 1 D2H)",
-                    "host_affinity": numa},
+                    "host_affinity": numa,
+                    "bound": "PCIe D2H of the step's outputs",
+                    "d2h_gbs_achieved": d2h * Ke / e2e_s / 1e9,
+                    "d2h_gbs_ceiling": pcie_d2h_gbs,
+                    "ceiling_note": "one pinned cudaMemcpy D2H of d2h_bytes_per_step + sync, measured in this run "
+                                    "on rank 0 (the e2e step adds the H2D of the actions, the kernel and the "
+                                    "Python wrapper)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(),
