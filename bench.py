@@ -467,7 +467,8 @@ def run_gpu(args):
     closed = None
     if args.closed_loop_steps > 0:
         closed = closed_loop(env, cfg, args.closed_loop_steps, dev)
-        closed["fused_actor"] = closed_loop_fused(cfg, args.envs, args.closed_loop_steps, local, rank)
+        closed["fused_actor"] = closed_loop_fused(cfg, args.envs, args.closed_loop_steps, local, rank,
+                                                  args.collect_streams)
 
     # ---- e2e through the numpy-facing drop-in ------------------------------------------------
     vec = GraphVecEnv(cfg, args.envs, device=local, env_offset=rank * args.envs, seed=1)
@@ -596,18 +597,20 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def closed_loop_fused(cfg, n_envs, n_steps, local, rank):
+def closed_loop_fused(cfg, n_envs, n_steps, local, rank, n_streams=1):
     """Closed loop with THIS library's actor kernel and C-level collect loop (f1):
     gsm_collect = per env step one graph_actor_kernel launch (forward + Gumbel-max sampling +
     log-prob, weights in the kernel parameter space) and one env-step launch, written straight into
     a [T+1]/[T] rollout buffer (f2); the 2T launches are replayed from a CUDA graph; the env is
     reset between rollouts.  Same declared actor architecture as the torch policy above."""
     import torch
-    from gs_marl_b200.environment import MultiAgentGraphConstrainEnv
+    from gs_marl_b200.environment import MultiAgentGraphConstrainEnv, StreamShardedEnv
     from gs_marl_b200.policy import GraphAttentionActor
     from gs_marl_b200.rollout import GraphRolloutBuffer, collect_fused
     dev = torch.device("cuda", local)
-    env = MultiAgentGraphConstrainEnv(cfg, n_envs, device=local, env_offset=rank * n_envs, seed=3)
+    env = (MultiAgentGraphConstrainEnv(cfg, n_envs, device=local, env_offset=rank * n_envs, seed=3)
+           if n_streams <= 1 else
+           StreamShardedEnv(cfg, n_envs, n_streams=n_streams, device=local, env_offset=rank * n_envs, seed=3))
     actor = GraphAttentionActor(len(cfg.discrete_u), seed=0)
     T = EPISODE_LEN
     buf = GraphRolloutBuffer(env, T)
@@ -653,7 +656,8 @@ def closed_loop_fused(cfg, n_envs, n_steps, local, rank):
     return {"value": n_envs * cfg.n_agents * reps * T / (ms * 1e-3), "unit": UNIT, "steps": reps * T,
             "ms_per_step": ms / (reps * T),
             "policy": "graph_actor_kernel<5> (this library, fp32, weights as kernel parameters) via gsm_collect; "
-                      f"CUDA graph of {2 * T} launches per {T}-step rollout + reset per rollout",
+                      f"CUDA graph of {2 * T} launches per {T}-step rollout per sub-shard ({max(1, n_streams)} "
+                      "sub-shard(s), each its own actor -> env chain on its own stream) + reset per rollout",
             "actor_kernel_us": actor_us, "mean_valid_rows_per_agent": rows / n_agents,
             "actor_tflops": flops / (actor_us * 1e-6) / 1e12,
             "actor_bound": "fp32 issue (FFMA with uniform-register weight operands); "
@@ -736,6 +740,8 @@ def main():
     ap.add_argument("--streams", type=int, default=4,
                     help="env sub-shards per GPU, each on its own CUDA stream (1 = one handle, one stream)")
     ap.add_argument("--closed-loop-steps", type=int, default=1000)
+    ap.add_argument("--collect-streams", type=int, default=1,
+                    help="env sub-shards (streams) of the fused closed loop: one shard's actor overlaps another's env step")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--ref-budget", type=float, default=90.0)
     ap.add_argument("--no-cpu", action="store_true")

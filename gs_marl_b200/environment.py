@@ -338,6 +338,10 @@ class StreamShardedEnv:
         parts = [sh.get_state() for sh in self.shards]
         return tuple(torch.cat([p[j] for p in parts], 0) for j in range(3))
 
+    def set_state(self, agent_state=None, landmark_pos=None, step_count=None):
+        for sh, (lo, hi) in zip(self.shards, self.bounds):
+            sh.set_state(*(None if x is None else x[lo:hi] for x in (agent_state, landmark_pos, step_count)))
+
     @property
     def kernel_launches(self) -> int:
         return sum(sh.kernel_launches for sh in self.shards)

@@ -37,14 +37,26 @@ class GraphRolloutBuffer:
             self.data[k] = torch.zeros((self.T,) + tuple(shape), dtype=_TORCH_DT[dt], device=dev)
         self.data["logp"] = torch.zeros((self.T,) + tuple(sh["reward"][1]), dtype=torch.float32, device=dev)
         self.step = 0
-        # slot 0 of every tensor: what gsm_collect takes (it strides through the slots itself)
-        io_all = abi.GsmStepIO()
-        for k in _OBS_KEYS + _STEP_KEYS + ("actions",):
-            setattr(io_all, k, self.data[k].data_ptr())
-        self._io_all = io_all
-        # one pre-built io struct per step: outputs of step t land in obs-slot t+1 / step-slot t
+        # a StreamShardedEnv is S handles over contiguous env ranges, each on its own stream, all
+        # filling THIS buffer (their slot stride is the whole env count: gsm_set_slot_envs)
+        self._shards = list(getattr(env, "shards", [env]))
+        self._bounds = list(getattr(env, "bounds", [(0, env.n_envs)]))
+        self._streams = list(getattr(env, "streams", [None] * len(self._shards)))
+        # per shard, slot 0 of every tensor at the shard's first env: what gsm_collect takes (it
+        # strides through the slots itself)
+        self._io_all, self._io_reset = [], []
+        for lo, hi in self._bounds:
+            io_all, io0 = abi.GsmStepIO(), abi.GsmStepIO()
+            for k in _OBS_KEYS + _STEP_KEYS + ("actions",):
+                setattr(io_all, k, self.data[k][0, lo:hi].data_ptr())
+            for k in _OBS_KEYS:
+                setattr(io0, k, self.data[k][0, lo:hi].data_ptr())
+            self._io_all.append(io_all)
+            self._io_reset.append(io0)
+        # one pre-built io struct per step (single-handle envs; `collect` with any torch policy):
+        # outputs of step t land in obs-slot t+1 / step-slot t
         self._io = []
-        for t in range(self.T):
+        for t in range(self.T if len(self._shards) == 1 else 0):
             io = abi.GsmStepIO()
             io.actions = self.data["actions"][t].data_ptr()
             for k in _OBS_KEYS:
@@ -52,10 +64,6 @@ class GraphRolloutBuffer:
             for k in _STEP_KEYS:
                 setattr(io, k, self.data[k][t].data_ptr())
             self._io.append(io)
-        io0 = abi.GsmStepIO()
-        for k in _OBS_KEYS:
-            setattr(io0, k, self.data[k][0].data_ptr())
-        self._io_reset = io0
 
     def __getitem__(self, k):
         return self.data[k]
@@ -63,11 +71,23 @@ class GraphRolloutBuffer:
     def graph(self, t: int) -> dict:
         return {k: self.data[k][t] for k in ("nbr_idx", "nbr_feat", "nbr_cnt", "adj")}
 
-    def reset_env(self):
-        """env.reset() with the first observation written straight into slot 0."""
+    def _on_shards(self, fn):
+        """fn(shard, shard_index, stream_ptr) on every shard's stream, current stream ordered
+        before and after (one handle: just the current stream)."""
         e = self.env
         with torch.cuda.device(e.device):
-            e._check(e.lib.gsm_reset(e._h, e._seed, None, 1, C.byref(self._io_reset), e._stream()))
+            if len(self._shards) == 1:
+                fn(self._shards[0], 0, self._shards[0]._stream())
+                return
+            e.fork()
+            for j, (sh, st) in enumerate(zip(self._shards, self._streams)):
+                fn(sh, j, C.c_void_p(st.cuda_stream))
+            e.join()
+
+    def reset_env(self):
+        """env.reset() with the first observation written straight into slot 0."""
+        self._on_shards(lambda sh, j, st: sh._check(
+            sh.lib.gsm_reset(sh._h, sh._seed, None, 1, C.byref(self._io_reset[j]), st)))
         self.step = 0
 
     def after_update(self):
@@ -80,6 +100,8 @@ class GraphRolloutBuffer:
 def collect(env: MultiAgentGraphConstrainEnv, policy: Callable, buf: GraphRolloutBuffer) -> GraphRolloutBuffer:
     """One rollout of buf.T steps: actions = policy(obs_t, graph_t) -> [n_envs, N(,2)] device
     tensor; the env step writes reward/cost/done of step t and obs/graph of t+1 into the buffer."""
+    if len(buf._shards) != 1:
+        raise ValueError("collect() drives one handle; use collect_fused() with a StreamShardedEnv")
     with torch.cuda.device(env.device):
         stream = env._stream()
         for t in range(buf.T):
@@ -95,29 +117,33 @@ def collect_fused(env: MultiAgentGraphConstrainEnv, actor, buf: GraphRolloutBuff
     """The same rollout with the actor forward + sampling as this library's kernel
     (`gsm_collect`: per step one actor launch and one env-step launch, enqueued from C with no
     Python or host sync in between; actions and log-probs land in the buffer slots).  `actor` is a
-    `policy.GraphAttentionActor`.  graph=True captures the 2·T launches into a CUDA graph and
+    `policy.GraphAttentionActor`.  With a `StreamShardedEnv` every sub-shard runs its own
+    actor -> env-step chain on its own stream into its env slice of the buffer, so one shard's actor
+    kernel (fp32-issue-bound) overlaps another's env step (HBM-bound).  graph=True captures the 2·T launches into a CUDA graph and
     returns it WITHOUT having advanced the env (replay runs the rollout from the env's current
     state and whatever slot 0 holds, with the Philox step counters and the weights baked in at
     capture: re-capture after an optimizer step)."""
     w = actor.packed()
+    logp = buf.data["logp"]
 
-    def enqueue(stream):
-        env._check(env.lib.gsm_collect(env._h, C.byref(w), buf.T, C.byref(buf._io_all),
-                                       C.c_void_p(buf.data["logp"].data_ptr()), int(seed), int(first_step),
-                                       int(bool(greedy)), stream))
+    def enqueue():
+        buf._on_shards(lambda sh, j, st: sh._check(sh.lib.gsm_collect(
+            sh._h, C.byref(w), buf.T, C.byref(buf._io_all[j]),
+            C.c_void_p(logp[0, buf._bounds[j][0]:].data_ptr()), int(seed), int(first_step),
+            int(bool(greedy)), st)))
     with torch.cuda.device(env.device):
         if not graph:
-            enqueue(env._stream())
+            enqueue()
             buf.step = buf.T
             return buf
         # one eager rollout first (module load / first-launch work must not happen inside a
         # capture); the env state is put back afterwards, slot 0 is never written by a collect
         saved = env.get_state()
-        enqueue(env._stream())
+        enqueue()
         env.set_state(*saved)
         torch.cuda.synchronize(env.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            enqueue(env._stream())
+            enqueue()
         buf.step = buf.T
         return g

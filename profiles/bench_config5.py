@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from gs_marl_b200 import scenarios  # noqa: E402
 from gs_marl_b200.env_wrappers import ShardedStats, shard_bounds  # noqa: E402
-from gs_marl_b200.environment import MultiAgentGraphConstrainEnv  # noqa: E402
+from gs_marl_b200.environment import MultiAgentGraphConstrainEnv, StreamShardedEnv  # noqa: E402
 from gs_marl_b200.policy import GraphAttentionActor  # noqa: E402
 from gs_marl_b200.rollout import GraphRolloutBuffer, collect, collect_fused  # noqa: E402
 
@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--agents", type=int, default=12)
     ap.add_argument("--rollouts", type=int, default=8)
     ap.add_argument("--T", type=int, default=25)
+    ap.add_argument("--streams", type=int, default=1, help="env sub-shards per GPU for the fused arm")
+    ap.add_argument("--arms", default="fused_actor,torch_policy")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -61,7 +63,10 @@ def main():
         torch.cuda.synchronize()
 
     def run(arm):
-        env = MultiAgentGraphConstrainEnv(cfg, n_envs, device=local, env_offset=lo, seed=11)
+        if arm == "fused_actor" and args.streams > 1:
+            env = StreamShardedEnv(cfg, n_envs, n_streams=args.streams, device=local, env_offset=lo, seed=11)
+        else:
+            env = MultiAgentGraphConstrainEnv(cfg, n_envs, device=local, env_offset=lo, seed=11)
         buf = GraphRolloutBuffer(env, T)
         buf.reset_env()
         if arm == "fused_actor":
@@ -99,7 +104,8 @@ def main():
                 "ms_per_step": ms.item() / steps, "steps": steps, "last_rollout_stats": tot,
                 "gsm_launches_rank0": launches}
 
-    res = {arm: run(arm) for arm in ("fused_actor", "torch_policy")}
+    res = {arm: run(arm) for arm in args.arms.split(",")}
+    res["fused_streams"] = args.streams
     if rank == 0:
         print(json.dumps({
             "config": f"BASELINE configs[4]: navigation, {N} agents, {args.envs} envs sharded over {world} GPU(s) "

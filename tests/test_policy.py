@@ -161,3 +161,31 @@ def test_gsm_collect_equals_stepwise_collect(scn, N):
         assert torch.equal(bufs[0][k], bufs[1][k]), k
         assert torch.equal(bufs[0][k], bufs[2][k]), k
     assert bufs[0]["actions"].float().std() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True])
+def test_collect_fused_over_stream_shards_equals_one_handle(graph):
+    """Sub-shards on their own streams (StreamShardedEnv) running their own actor -> env chains fill
+    the same buffer with exactly what one handle produces: resets and Gumbel draws are keyed by the
+    global env / agent index."""
+    from gs_marl_b200.environment import MultiAgentGraphConstrainEnv, StreamShardedEnv
+    from gs_marl_b200.rollout import GraphRolloutBuffer, collect_fused
+    cfg = make_cfg("navigation", 3, "f32")
+    actor = GraphAttentionActor(len(cfg.discrete_u), seed=13)
+    T, n_envs = 6, 1000
+    outs = []
+    for S in (1, 3):
+        env = (MultiAgentGraphConstrainEnv(cfg, n_envs, env_offset=7, seed=9) if S == 1 else
+               StreamShardedEnv(cfg, n_envs, n_streams=S, env_offset=7, seed=9))
+        buf = GraphRolloutBuffer(env, T)
+        buf.reset_env()
+        r = collect_fused(env, actor, buf, seed=3, first_step=50, graph=graph)
+        if graph:
+            buf["actions"].zero_(); buf["logp"].zero_()
+            r.replay()
+        torch.cuda.synchronize()
+        outs.append({k: v.clone() for k, v in buf.data.items()})
+        env.close()
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
