@@ -615,7 +615,7 @@ def closed_loop_fused(cfg, n_envs, n_steps, local, rank, n_streams=1):
     T = EPISODE_LEN
     buf = GraphRolloutBuffer(env, T)
     buf.reset_env()
-    g = collect_fused(env, actor, buf, seed=1, first_step=0, graph=True)
+    g = collect_fused(env, actor, buf, seed=1, first_step=0, graph=True, with_values=False)
     for _ in range(2):
         g.replay(); buf.reset_env()
     torch.cuda.synchronize()

@@ -8,13 +8,14 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-GSM_ABI_VERSION = 6
+GSM_ABI_VERSION = 7
 GSM_OBS_DIM = 6
 GSM_NBR_FEAT_DIM = 6
 GSM_MAX_DISCRETE = 16
 GSM_MAX_LSA_N = 32
 GSM_POLICY_HIDDEN = 64
 GSM_POLICY_MAX_ACTIONS = 9
+GSM_POLICY_VALUE_HEADS = 2
 
 GSM_F32, GSM_F64 = 0, 1
 GSM_SCN_NAVIGATION, GSM_SCN_POLYGON, GSM_SCN_LINE = 0, 1, 2
@@ -70,6 +71,7 @@ class GsmPolicyWeights(C.Structure):
         ("nbr_w", C.c_float * GSM_NBR_FEAT_DIM * _H), ("nbr_b", C.c_float * _H),
         ("att_w", C.c_float * _H), ("att_b", C.c_float),
         ("head_w", C.c_float * (2 * _H) * _A), ("head_b", C.c_float * _A),
+        ("value_w", C.c_float * (2 * _H) * GSM_POLICY_VALUE_HEADS), ("value_b", C.c_float * GSM_POLICY_VALUE_HEADS),
     ]
 
 
@@ -77,7 +79,7 @@ class GsmPolicyIO(C.Structure):
     _fields_ = [
         ("obs", C.c_void_p), ("nbr_feat", C.c_void_p), ("nbr_cnt", C.c_void_p),
         ("actions", C.c_void_p), ("logp", C.c_void_p), ("logits", C.c_void_p),
-        ("n_rows", C.c_int64), ("row_offset", C.c_uint64), ("seed", C.c_uint64), ("step", C.c_uint64),
+        ("values", C.c_void_p), ("n_rows", C.c_int64), ("row_offset", C.c_uint64), ("seed", C.c_uint64), ("step", C.c_uint64),
         ("max_nbrs", C.c_int32), ("greedy", C.c_int32),
     ]
 
@@ -112,8 +114,8 @@ SYMBOLS = {
                           C.c_void_p]),
     "gsm_policy_act": (C.c_int, [C.POINTER(GsmPolicyWeights), C.POINTER(GsmPolicyIO), C.c_int, C.c_void_p]),
     "gsm_policy_last_error": (C.c_char_p, []),
-    "gsm_collect": (C.c_int, [_H, C.POINTER(GsmPolicyWeights), C.c_int32, _IO, C.c_void_p, C.c_uint64,
-                              C.c_uint64, C.c_int32, C.c_void_p]),
+    "gsm_collect": (C.c_int, [_H, C.POINTER(GsmPolicyWeights), C.c_int32, _IO, C.c_void_p, C.c_void_p,
+                              C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libgsmarl_b200.so")

@@ -604,7 +604,8 @@ int gsm_get_state_host(gsm_env* h, void* agent_state, void* landmark_pos, int32_
 }
 
 int gsm_collect(gsm_env* h, const gsm_policy_weights* w, int32_t n_steps, const gsm_step_io* io,
-                float* logp, uint64_t seed, uint64_t first_step, int32_t greedy, void* stream) {
+                float* logp, float* values, uint64_t seed, uint64_t first_step, int32_t greedy,
+                void* stream) {
   if (!h || !io || !w || n_steps < 1) return GSM_ERR_INVALID_ARG;
   if (!is_f32(h) || h->hp.action_mode != GSM_ACT_DISCRETE)
     return fail(h, GSM_ERR_UNSUPPORTED, "gsm_collect needs a GSM_F32 handle with discrete actions");
@@ -630,6 +631,7 @@ int gsm_collect(gsm_env* h, const gsm_policy_weights* w, int32_t n_steps, const 
     pio.actions = (int32_t*)const_cast<void*>(cur.actions);
     pio.logp = logp ? logp + (size_t)t * slot_rows : nullptr;
     pio.logits = nullptr;
+    pio.values = values ? values + (size_t)t * slot_rows * GSM_POLICY_VALUE_HEADS : nullptr;
     pio.n_rows = rows;
     pio.row_offset = (uint64_t)h->hp.env_offset * (uint64_t)h->hp.N;
     pio.seed = seed; pio.step = first_step + (uint64_t)t;

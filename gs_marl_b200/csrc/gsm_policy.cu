@@ -4,7 +4,7 @@
 //
 // Reference side (withheld): the GNN encoder of gsmarl/algorithms/* over torch-geometric
 // (requirements.txt:119) called from runner/mpe_runner.py's collect (SOURCES.txt:28).  The
-// architecture is therefore DECLARED (SPEC.md §9), not GS-MARL's: shared parameters over agents,
+// architecture is therefore DECLARED (SPEC.md §10), not GS-MARL's: shared parameters over agents,
 //   e   = relu(W_e obs + b_e)                               [H]
 //   m_r = relu(W_n feat_r + b_n),  r < cnt                  [H] per valid neighbour row
 //   a_r = softmax_r(w_a . m_r + b_a)                        masked to the cnt valid rows
@@ -37,14 +37,15 @@ struct PolicyParams {                 // kernel-parameter image of gsm_policy_we
   float nbr_w[H][GSM_NBR_FEAT_DIM];
   float nbr_b[H];
   float att_w[H];
-  float head_w[GSM_POLICY_MAX_ACTIONS][2 * H];
-  float head_b[GSM_POLICY_MAX_ACTIONS];
+  // rows 0..NA-1: action logits; rows NA, NA+1: the two critics (reward value, cost value)
+  float head_w[GSM_POLICY_MAX_ACTIONS + GSM_POLICY_VALUE_HEADS][2 * H];
+  float head_b[GSM_POLICY_MAX_ACTIONS + GSM_POLICY_VALUE_HEADS];
   float att_b;
 };
 
 struct PolicyIO {
   const float* obs; const float* nbr_feat; const int32_t* nbr_cnt;
-  int32_t* actions; float* logp; float* logits;
+  int32_t* actions; float* logp; float* logits; float* values;
   int64_t n_rows; uint64_t row_offset, seed, step;
   int K, greedy;
 };
@@ -62,7 +63,9 @@ __device__ __forceinline__ void philox_p(uint32_t c0, uint32_t c1, uint32_t c2, 
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-template <int NA>
+// NV = 0: actor only; NV = GSM_POLICY_VALUE_HEADS: the critics ride along as NV more rows of the head
+// (+2 FFMA per hidden unit and row), for collect loops that store value predictions.
+template <int NA, int NV>
 __global__ void __launch_bounds__(128)
 graph_actor_kernel(const __grid_constant__ PolicyParams w, const __grid_constant__ PolicyIO io) {
   // The row loop runs cnt times and cnt differs from agent to agent (0..K): a warp would pay for
@@ -103,9 +106,10 @@ graph_actor_kernel(const __grid_constant__ PolicyParams w, const __grid_constant
   const int64_t i = base + (slot & 0xff);
   const int cnt = slot >> 8;
 
-  float z[NA];
+  constexpr int NZ = NA + NV;
+  float z[NZ];
 #pragma unroll
-  for (int a = 0; a < NA; a++) z[a] = w.head_b[a];
+  for (int a = 0; a < NZ; a++) z[a] = w.head_b[a];
 
   {  // ego branch
     const float2* o2 = reinterpret_cast<const float2*>(io.obs + i * GSM_OBS_DIM);
@@ -118,23 +122,23 @@ graph_actor_kernel(const __grid_constant__ PolicyParams w, const __grid_constant
       e = fmaf(w.ego_w[j][4], o45.x, e); e = fmaf(w.ego_w[j][5], o45.y, e);
       e = fmaxf(e, 0.f);
 #pragma unroll
-      for (int a = 0; a < NA; a++) z[a] = fmaf(w.head_w[a][j], e, z[a]);
+      for (int a = 0; a < NZ; a++) z[a] = fmaf(w.head_w[a][j], e, z[a]);
     }
   }
 
   // neighbour rows: online softmax over the attention score, W_h's second half applied per row
-  float mx = -__int_as_float(0x7f800000), s = 0.f, acc[NA];
+  float mx = -__int_as_float(0x7f800000), s = 0.f, acc[NZ];
 #pragma unroll
-  for (int a = 0; a < NA; a++) acc[a] = 0.f;
+  for (int a = 0; a < NZ; a++) acc[a] = 0.f;
   const float2* f2 = reinterpret_cast<const float2*>(io.nbr_feat + i * (int64_t)io.K * GSM_NBR_FEAT_DIM);
   float2 n01, n23, n45;                 // next row, loaded one iteration ahead
   if (cnt > 0) { n01 = f2[0]; n23 = f2[1]; n45 = f2[2]; }
   for (int r = 0; r < cnt; r++) {
     const float2 f01 = n01, f23 = n23, f45 = n45;
     if (r + 1 < cnt) { n01 = f2[3 * r + 3]; n23 = f2[3 * r + 4]; n45 = f2[3 * r + 5]; }
-    float t = w.att_b, hr[NA];
+    float t = w.att_b, hr[NZ];
 #pragma unroll
-    for (int a = 0; a < NA; a++) hr[a] = 0.f;
+    for (int a = 0; a < NZ; a++) hr[a] = 0.f;
 #pragma unroll
     for (int j = 0; j < H; j++) {
       float m = w.nbr_b[j];
@@ -144,19 +148,23 @@ graph_actor_kernel(const __grid_constant__ PolicyParams w, const __grid_constant
       m = fmaxf(m, 0.f);
       t = fmaf(w.att_w[j], m, t);
 #pragma unroll
-      for (int a = 0; a < NA; a++) hr[a] = fmaf(w.head_w[a][H + j], m, hr[a]);
+      for (int a = 0; a < NZ; a++) hr[a] = fmaf(w.head_w[a][H + j], m, hr[a]);
     }
     const float nm = fmaxf(mx, t);
     const float sc = expf(mx - nm), p = expf(t - nm);   // first row: exp(-inf) = 0
     s = fmaf(s, sc, p);
 #pragma unroll
-    for (int a = 0; a < NA; a++) acc[a] = fmaf(acc[a], sc, p * hr[a]);
+    for (int a = 0; a < NZ; a++) acc[a] = fmaf(acc[a], sc, p * hr[a]);
     mx = nm;
   }
   if (cnt > 0) {
     const float inv = 1.f / s;
 #pragma unroll
-    for (int a = 0; a < NA; a++) z[a] = fmaf(acc[a], inv, z[a]);
+    for (int a = 0; a < NZ; a++) z[a] = fmaf(acc[a], inv, z[a]);
+  }
+  if (NV > 0) {
+#pragma unroll
+    for (int v = 0; v < NV; v++) io.values[i * NV + v] = z[NA + v];
   }
 
   if (io.logits) {
@@ -205,11 +213,13 @@ static int launch_actor(const PolicyParams& w, const PolicyIO& io, int n_actions
   if (io.n_rows == 0) return 0;
   const int block = 128;            // the kernel's counting sort assumes exactly 128
   const int64_t grid = (io.n_rows + block - 1) / block;
-  switch (n_actions) {
-    case 5: graph_actor_kernel<5><<<(unsigned)grid, block, 0, st>>>(w, io); break;
-    case 9: graph_actor_kernel<9><<<(unsigned)grid, block, 0, st>>>(w, io); break;
-    default: return -1;
-  }
+  constexpr int V = GSM_POLICY_VALUE_HEADS;
+  const unsigned gd = (unsigned)grid;
+  if (n_actions == 5 && !io.values) graph_actor_kernel<5, 0><<<gd, block, 0, st>>>(w, io);
+  else if (n_actions == 5) graph_actor_kernel<5, V><<<gd, block, 0, st>>>(w, io);
+  else if (n_actions == 9 && !io.values) graph_actor_kernel<9, 0><<<gd, block, 0, st>>>(w, io);
+  else if (n_actions == 9) graph_actor_kernel<9, V><<<gd, block, 0, st>>>(w, io);
+  else return -1;
   return (int)cudaGetLastError();
 }
 
@@ -227,11 +237,15 @@ int pack(const gsm_policy_weights* w, gsm::PolicyParams* p) {
   if (w->struct_size != sizeof(gsm_policy_weights)) return pfail(GSM_ERR_ABI, "gsm_policy: weights.struct_size mismatch");
   if (w->n_actions != 5 && w->n_actions != 9)
     return pfail(GSM_ERR_UNSUPPORTED, "gsm_policy: compiled actor instances exist for n_actions 5 and 9 only");
-  static_assert(sizeof(p->ego_w) == sizeof(w->ego_w) && sizeof(p->head_w) == sizeof(w->head_w), "layout");
+  static_assert(sizeof(p->ego_w) == sizeof(w->ego_w), "layout");
   std::memcpy(p->ego_w, w->ego_w, sizeof(p->ego_w));   std::memcpy(p->ego_b, w->ego_b, sizeof(p->ego_b));
   std::memcpy(p->nbr_w, w->nbr_w, sizeof(p->nbr_w));   std::memcpy(p->nbr_b, w->nbr_b, sizeof(p->nbr_b));
   std::memcpy(p->att_w, w->att_w, sizeof(p->att_w));   p->att_b = w->att_b;
-  std::memcpy(p->head_w, w->head_w, sizeof(p->head_w)); std::memcpy(p->head_b, w->head_b, sizeof(p->head_b));
+  std::memset(p->head_w, 0, sizeof(p->head_w)); std::memset(p->head_b, 0, sizeof(p->head_b));
+  std::memcpy(p->head_w, w->head_w, sizeof(float) * 2 * GSM_POLICY_HIDDEN * w->n_actions);
+  std::memcpy(p->head_b, w->head_b, sizeof(float) * w->n_actions);
+  std::memcpy(p->head_w[w->n_actions], w->value_w, sizeof(w->value_w));   // critics right behind the logits' rows
+  std::memcpy(&p->head_b[w->n_actions], w->value_b, sizeof(w->value_b));
   return GSM_OK;
 }
 struct DevGuard {
@@ -261,7 +275,7 @@ int gsm_policy_act(const gsm_policy_weights* w, const gsm_policy_io* io, int dev
   DevGuard guard(device);
   gsm::PolicyIO k;
   k.obs = io->obs; k.nbr_feat = io->nbr_feat; k.nbr_cnt = io->nbr_cnt;
-  k.actions = io->actions; k.logp = io->logp; k.logits = io->logits;
+  k.actions = io->actions; k.logp = io->logp; k.logits = io->logits; k.values = io->values;
   k.n_rows = io->n_rows; k.row_offset = io->row_offset; k.seed = io->seed; k.step = io->step;
   k.K = io->max_nbrs; k.greedy = io->greedy;
   const int e = gsm::launch_actor(p, k, w->n_actions, (cudaStream_t)stream);

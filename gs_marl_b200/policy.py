@@ -1,7 +1,7 @@
 """Graph-attention actor over the env's padded neighbour rows — SURVEY.md §8 row f3 (the GNN
 encoder forward of gsmarl/algorithms over torch-geometric, requirements.txt:119; withheld).
 
-The architecture is the DECLARED one of SPEC.md §9 (the reference's is unknown): parameters
+The architecture is the DECLARED one of SPEC.md §10 (the reference's is unknown): parameters
 shared by all agents,
     e = relu(W_e obs + b_e);  m_r = relu(W_n feat_r + b_n) for the nbr_cnt valid rows;
     a = softmax_r(w_a . m_r + b_a);  z = W_h [e ; sum_r a_r m_r] + b_h;
@@ -43,6 +43,7 @@ class GraphAttentionActor(torch.nn.Module):
         self.nbr = lin(H, abi.GSM_NBR_FEAT_DIM)
         self.att = lin(1, H)
         self.head = lin(n_actions, 2 * H)
+        self.value = lin(abi.GSM_POLICY_VALUE_HEADS, 2 * H)     # [0] reward critic, [1] cost critic
         self._packed = None
 
     # ---- weights -> the C struct (host memory; they ride in the kernel's parameter space) ----
@@ -63,6 +64,7 @@ class GraphAttentionActor(torch.nn.Module):
         put("att_w", self.att.weight.reshape(-1))
         w.att_b = float(self.att.bias.item())
         put("head_w", self.head.weight, self.n_actions); put("head_b", self.head.bias, self.n_actions)
+        put("value_w", self.value.weight); put("value_b", self.value.bias)
         self._packed = w
         return w
 
@@ -73,9 +75,10 @@ class GraphAttentionActor(torch.nn.Module):
     # ---- collect path: one kernel ------------------------------------------------------------
     @torch.no_grad()
     def act(self, obs, graph, seed: int = 0, step: int = 0, row_offset: int = 0, greedy: bool = False,
-            want_logits: bool = False, out=None):
+            want_logits: bool = False, want_values: bool = False, out=None):
         """obs [..., 6], graph['nbr_feat'] [..., K, 6], graph['nbr_cnt'] [...] (fp32 / int32 CUDA
-        tensors, contiguous) -> actions int32 [...], logp fp32 [...], (logits [..., n_actions])."""
+        tensors, contiguous) -> actions int32 [...], logp fp32 [...], then logits [..., n_actions] if
+        want_logits, then values [..., 2] (reward critic, cost critic) if want_values."""
         lib = abi.load_library()
         feat, cnt = graph["nbr_feat"], graph["nbr_cnt"]
         if not obs.is_cuda:
@@ -99,16 +102,25 @@ class GraphAttentionActor(torch.nn.Module):
         io.obs, io.nbr_feat, io.nbr_cnt = obs.data_ptr(), feat.data_ptr(), cnt.data_ptr()
         io.actions, io.logp = actions.data_ptr(), logp.data_ptr()
         io.logits = logits.data_ptr() if want_logits else None
+        values = (torch.empty(lead + (abi.GSM_POLICY_VALUE_HEADS,), dtype=torch.float32, device=dev)
+                  if want_values else None)
+        io.values = values.data_ptr() if want_values else None
         io.n_rows, io.row_offset, io.seed, io.step = n_rows, int(row_offset), int(seed), int(step)
         io.max_nbrs, io.greedy = int(feat.shape[-2]), int(bool(greedy))
         st = lib.gsm_policy_act(C.byref(self.packed()), C.byref(io), dev.index or 0,
                                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         if st != 0:
             raise abi.GsmError(f"{lib.gsm_status_string(st).decode()}: {lib.gsm_policy_last_error().decode()}")
-        return (actions, logp, logits) if want_logits else (actions, logp)
+        return (actions, logp) + ((logits,) if want_logits else ()) + ((values,) if want_values else ())
 
     # ---- learner path: same function, differentiable (not used by act / collect_fused) --------
     def logits_autograd(self, obs, graph):
+        return self.head(self.embed_autograd(obs, graph))
+
+    def values_autograd(self, obs, graph):
+        return self.value(self.embed_autograd(obs, graph))
+
+    def embed_autograd(self, obs, graph):
         feat, cnt = graph["nbr_feat"], graph["nbr_cnt"]
         K = feat.shape[-2]
         e = torch.relu(self.ego(obs))
@@ -117,4 +129,4 @@ class GraphAttentionActor(torch.nn.Module):
         sc = self.att(m).squeeze(-1).masked_fill(~valid, float("-inf"))
         a = torch.softmax(sc, -1).nan_to_num(0.0)            # rows with cnt == 0: all -inf -> 0
         agg = (a[..., None] * m).sum(-2)
-        return self.head(torch.cat([e, agg], -1))
+        return torch.cat([e, agg], -1)

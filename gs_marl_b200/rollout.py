@@ -36,6 +36,10 @@ class GraphRolloutBuffer:
             dt, shape = sh[k]
             self.data[k] = torch.zeros((self.T,) + tuple(shape), dtype=_TORCH_DT[dt], device=dev)
         self.data["logp"] = torch.zeros((self.T,) + tuple(sh["reward"][1]), dtype=torch.float32, device=dev)
+        # critics' predictions for the observation of slot t (value_preds / cost_preds of the lineage's
+        # buffers); slot T is filled by the caller's bootstrap forward on the last observation
+        self.data["values"] = torch.zeros((self.T + 1,) + tuple(sh["reward"][1]) + (abi.GSM_POLICY_VALUE_HEADS,),
+                                          dtype=torch.float32, device=dev)
         self.step = 0
         # a StreamShardedEnv is S handles over contiguous env ranges, each on its own stream, all
         # filling THIS buffer (their slot stride is the whole env count: gsm_set_slot_envs)
@@ -113,10 +117,11 @@ def collect(env: MultiAgentGraphConstrainEnv, policy: Callable, buf: GraphRollou
 
 
 def collect_fused(env: MultiAgentGraphConstrainEnv, actor, buf: GraphRolloutBuffer, seed: int = 0,
-                  first_step: int = 0, greedy: bool = False, graph: bool = False):
+                  first_step: int = 0, greedy: bool = False, graph: bool = False, with_values: bool = True):
     """The same rollout with the actor forward + sampling as this library's kernel
     (`gsm_collect`: per step one actor launch and one env-step launch, enqueued from C with no
-    Python or host sync in between; actions and log-probs land in the buffer slots).  `actor` is a
+    Python or host sync in between; actions, log-probs and — with_values — the two critics'
+    predictions land in the buffer slots).  `actor` is a
     `policy.GraphAttentionActor`.  With a `StreamShardedEnv` every sub-shard runs its own
     actor -> env-step chain on its own stream into its env slice of the buffer, so one shard's actor
     kernel (fp32-issue-bound) overlaps another's env step (HBM-bound).  graph=True captures the 2·T launches into a CUDA graph and
@@ -124,12 +129,13 @@ def collect_fused(env: MultiAgentGraphConstrainEnv, actor, buf: GraphRolloutBuff
     state and whatever slot 0 holds, with the Philox step counters and the weights baked in at
     capture: re-capture after an optimizer step)."""
     w = actor.packed()
-    logp = buf.data["logp"]
+    logp, values = buf.data["logp"], buf.data["values"]
 
     def enqueue():
         buf._on_shards(lambda sh, j, st: sh._check(sh.lib.gsm_collect(
             sh._h, C.byref(w), buf.T, C.byref(buf._io_all[j]),
-            C.c_void_p(logp[0, buf._bounds[j][0]:].data_ptr()), int(seed), int(first_step),
+            C.c_void_p(logp[0, buf._bounds[j][0]:].data_ptr()),
+            C.c_void_p(values[0, buf._bounds[j][0]:].data_ptr()) if with_values else None, int(seed), int(first_step),
             int(bool(greedy)), st)))
     with torch.cuda.device(env.device):
         if not graph:

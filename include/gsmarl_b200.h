@@ -33,14 +33,15 @@
 extern "C" {
 #endif
 
-#define GSM_ABI_VERSION 6
+#define GSM_ABI_VERSION 7
 
 #define GSM_OBS_DIM 6        /* vx, vy, px, py, target_dx, target_dy          (SPEC.md §6) */
 #define GSM_NBR_FEAT_DIM 6   /* dx, dy, dvx, dvy, dist, (real)entity_type     (SPEC.md §6) */
 #define GSM_MAX_DISCRETE 16
 #define GSM_MAX_LSA_N 32     /* one warp lane per assignment column */
-#define GSM_POLICY_HIDDEN 64       /* hidden width of the declared graph actor (SPEC.md §9) */
+#define GSM_POLICY_HIDDEN 64       /* hidden width of the declared graph actor (SPEC.md §10) */
 #define GSM_POLICY_MAX_ACTIONS 9   /* rows of head_w; compiled instances: n_actions 5 and 9  */
+#define GSM_POLICY_VALUE_HEADS 2   /* critics on the same embedding: reward value, cost value */
 
 typedef enum gsm_status {
   GSM_OK = 0,
@@ -237,7 +238,7 @@ int gsm_lsa(const void* cost, int32_t* col4row, int64_t n_problems, int32_t n,
  * Reference side (withheld): the GNN actor of gsmarl/algorithms (torch-geometric,
  * requirements.txt:119) evaluated once per env step by runner/mpe_runner.py's collect
  * (SOURCES.txt:28), whose results go into utils/graph_separated_buffer.py (SOURCES.txt:33).
- * The architecture is the DECLARED one of SPEC.md §9 (parameters shared by all agents):
+ * The architecture is the DECLARED one of SPEC.md §10 (parameters shared by all agents):
  *   e = relu(ego_w obs + ego_b); m_r = relu(nbr_w feat_r + nbr_b) for the nbr_cnt valid rows;
  *   a = softmax_r(att_w . m_r + att_b); z = head_w [e ; sum_r a_r m_r] + head_b;
  *   action = argmax_k(z_k - log(-log(u_k))), u from Philox4x32-10 with key = seed and counter
@@ -255,6 +256,8 @@ typedef struct gsm_policy_weights {
   float att_b;
   float head_w[GSM_POLICY_MAX_ACTIONS][2 * GSM_POLICY_HIDDEN];   /* rows >= n_actions ignored */
   float head_b[GSM_POLICY_MAX_ACTIONS];
+  float value_w[GSM_POLICY_VALUE_HEADS][2 * GSM_POLICY_HIDDEN];  /* v = value_w [e ; sum_r a_r m_r] + value_b */
+  float value_b[GSM_POLICY_VALUE_HEADS];                         /* [0] reward critic, [1] cost critic   */
 } gsm_policy_weights;
 
 typedef struct gsm_policy_io {   /* DEVICE pointers; a "row" is one agent of one env */
@@ -264,6 +267,7 @@ typedef struct gsm_policy_io {   /* DEVICE pointers; a "row" is one agent of one
   int32_t* actions;        /* [n_rows]  out                             */
   float* logp;             /* [n_rows]  out, log pi(action); NULL = skip */
   float* logits;           /* [n_rows][n_actions] out; NULL = skip       */
+  float* values;           /* [n_rows][GSM_POLICY_VALUE_HEADS] out; NULL = skip (actor-only kernel) */
   int64_t n_rows;
   uint64_t row_offset;     /* global index of row 0 (env_offset * N): sharding-invariant draws */
   uint64_t seed, step;
@@ -278,14 +282,17 @@ const char* gsm_policy_last_error(void);
  * kernels per step; capturable into a CUDA graph).  io->obs / nbr_* / adj / assign point at slot 0
  * of [n_steps+1][...] tensors whose slot 0 already holds the current observation (gsm_reset,
  * gsm_observe or the previous collect's last slot); io->actions / reward / cost / done point at
- * slot 0 of [n_steps][...] tensors; logp: float [n_steps][n_envs][N] or NULL.  Step t: the actor
+ * slot 0 of [n_steps][...] tensors; logp: float [n_steps][n_envs][N] or NULL; values: float
+ * [n_steps][n_envs][N][GSM_POLICY_VALUE_HEADS] or NULL (the critics' predictions for the observation
+ * the action was taken in — the buffer's value_preds / cost_preds).  Step t: the actor
  * reads observation slot t and writes actions (and logp) slot t with Philox step first_step + t;
  * gsm_step writes reward / cost / done slot t and the next observation into slot t + 1 — the
  * buffer "insert" is where the kernels write.  Slot strides follow gsm_get_io_sizes /
  * gsm_set_slot_envs.  Needs a GSM_F32, GSM_ACT_DISCRETE handle with n_discrete_actions ==
  * w->n_actions. */
 int gsm_collect(gsm_env* h, const gsm_policy_weights* w, int32_t n_steps, const gsm_step_io* io,
-                float* logp, uint64_t seed, uint64_t first_step, int32_t greedy, void* stream);
+                float* logp, float* values, uint64_t seed, uint64_t first_step, int32_t greedy,
+                void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,9 +1,9 @@
-"""TEST INFRASTRUCTURE — numpy restatement of the declared graph actor (SPEC.md §9) that
+"""TEST INFRASTRUCTURE — numpy restatement of the declared graph actor (SPEC.md §10) that
 gs_marl_b200/csrc/gsm_policy.cu implements.  Only tests/, smoke() and
 bench.py's checker legs may import this.
 
 PARITY UNPINNED: the reference's GNN actor (gsmarl/algorithms/*, torch-geometric per
-requirements.txt:119) is withheld, so this restates SPEC.md §9, not GS-MARL.  What IS pinned:
+requirements.txt:119) is withheld, so this restates SPEC.md §10, not GS-MARL.  What IS pinned:
 Philox4x32-10 (to the C oracle's, which is pinned to the Random123 known-answer vectors) and
 the forward pass to an independent plain-torch fp32 formulation (tests/test_policy.py).
 """
@@ -32,11 +32,21 @@ def weights_from_state_dict(sd, dtype=np.float32):
     g = lambda k: np.asarray(sd[k].detach().cpu().numpy() if hasattr(sd[k], "detach") else sd[k], dtype=dtype)
     return {"ego_w": g("ego.weight"), "ego_b": g("ego.bias"), "nbr_w": g("nbr.weight"), "nbr_b": g("nbr.bias"),
             "att_w": g("att.weight").reshape(-1), "att_b": g("att.bias").reshape(()),
-            "head_w": g("head.weight"), "head_b": g("head.bias")}
+            "head_w": g("head.weight"), "head_b": g("head.bias"),
+            "value_w": g("value.weight"), "value_b": g("value.bias")}
 
 
 def logits(w, obs, nbr_feat, nbr_cnt, dtype=np.float64):
-    """SPEC.md §9 forward.  obs [R,6], nbr_feat [R,K,6], nbr_cnt [R] -> [R, n_actions]."""
+    """SPEC.md §10 forward.  obs [R,6], nbr_feat [R,K,6], nbr_cnt [R] -> [R, n_actions]."""
+    return forward(w, obs, nbr_feat, nbr_cnt, dtype)[0]
+
+
+def values(w, obs, nbr_feat, nbr_cnt, dtype=np.float64):
+    """The two critics (reward value, cost value) on the same embedding -> [R, 2]."""
+    return forward(w, obs, nbr_feat, nbr_cnt, dtype)[1]
+
+
+def forward(w, obs, nbr_feat, nbr_cnt, dtype=np.float64):
     w = {k: np.asarray(v, dtype=dtype) for k, v in w.items()}
     obs, feat = np.asarray(obs, dtype=dtype), np.asarray(nbr_feat, dtype=dtype)
     R, K = feat.shape[0], feat.shape[1]
@@ -52,7 +62,8 @@ def logits(w, obs, nbr_feat, nbr_cnt, dtype=np.float64):
     s = p.sum(1)
     a = p / np.where(s > 0, s, 1.0)[:, None]
     agg = (a[..., None] * m).sum(1)                                     # zero when cnt == 0
-    return e @ w["head_w"][:, :Hh].T + agg @ w["head_w"][:, Hh:].T + w["head_b"]
+    emb = np.concatenate([e, agg], 1)
+    return emb @ w["head_w"].T + w["head_b"], emb @ w["value_w"].T + w["value_b"]
 
 
 def gumbel(n_rows, n_actions, seed, step, row_offset=0):

@@ -70,7 +70,7 @@ def main():
         buf = GraphRolloutBuffer(env, T)
         buf.reset_env()
         if arm == "fused_actor":
-            g = collect_fused(env, actor, buf, seed=5, graph=True)
+            g = collect_fused(env, actor, buf, seed=5, graph=True, with_values=False)   # same work as the torch arm
             once = g.replay
         else:
             @torch.no_grad()

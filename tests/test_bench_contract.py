@@ -44,3 +44,7 @@ def test_gpu_arm_line():
     assert d["e2e"]["value"] < d["value"]              # the host path cannot beat the device path
     assert d["cpu_baseline"]["kind"] == "port" and d["dtype"] == "f32" and d["scaling"] == "weak"
     assert d["config"]["workload"].startswith("cooperative navigation, 3 agents, 16384 envs")
+    e = d["e2e"]
+    assert 0 < e["d2h_gbs_achieved"] < e["d2h_gbs_ceiling"] * 1.05      # below the measured pinned-copy rate
+    f = d["closed_loop"]["fused_actor"]
+    assert f["value"] > d["closed_loop"]["value"] and f["actor_kernel_us"] > 0

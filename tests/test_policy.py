@@ -1,4 +1,4 @@
-"""the declared graph actor (SPEC.md §9) and the fused collect loop.
+"""the declared graph actor (SPEC.md §10) and the fused collect loop.
 
 CPU: the numpy oracle against an independent plain-torch fp32 formulation, numpy Philox against
 the C oracle's (Random123-pinned).  GPU: `gsm_policy_act` against the oracle (logits, log-probs,
@@ -45,6 +45,10 @@ def test_oracle_matches_torch_formulation(n_actions):
         zt = actor.logits_autograd(torch.from_numpy(obs), {"nbr_feat": torch.from_numpy(feat),
                                                            "nbr_cnt": torch.from_numpy(cnt)}).numpy()
     np.testing.assert_allclose(z, zt, rtol=1e-4, atol=1e-5)
+    with torch.no_grad():
+        vt = actor.values_autograd(torch.from_numpy(obs), {"nbr_feat": torch.from_numpy(feat),
+                                                           "nbr_cnt": torch.from_numpy(cnt)}).numpy()
+    np.testing.assert_allclose(P.values(w, obs, feat, cnt), vt, rtol=1e-4, atol=1e-5)
     # padded rows must not matter: garbage in them leaves the logits unchanged
     junk = feat.copy()
     junk[np.arange(8)[None, :] >= cnt[:, None]] = 1e3
@@ -54,11 +58,13 @@ def test_oracle_matches_torch_formulation(n_actions):
 def test_pack_layout_roundtrip():
     actor = GraphAttentionActor(5, seed=4)
     w = actor.pack()
-    assert w.struct_size == C.sizeof(abi.GsmPolicyWeights) == 8496 and w.n_actions == 5
+    assert w.struct_size == C.sizeof(abi.GsmPolicyWeights) == 9528 and w.n_actions == 5
     np.testing.assert_array_equal(np.ctypeslib.as_array(w.ego_w), actor.ego.weight.detach().numpy())
     np.testing.assert_array_equal(np.ctypeslib.as_array(w.head_w)[:5], actor.head.weight.detach().numpy())
     assert np.all(np.ctypeslib.as_array(w.head_w)[5:] == 0)
     assert abs(w.att_b - actor.att.bias.item()) < 1e-7
+    np.testing.assert_array_equal(np.ctypeslib.as_array(w.value_w), actor.value.weight.detach().numpy())
+    assert C.sizeof(abi.GsmPolicyIO) == 96
 
 
 def test_policy_bad_arguments_without_device():
@@ -86,7 +92,17 @@ def test_actor_kernel_matches_oracle(n_actions, R, K):
     w = P.weights_from_state_dict(actor.state_dict())
     dev = torch.device("cuda", 0)
     g = {"nbr_feat": torch.from_numpy(feat).to(dev), "nbr_cnt": torch.from_numpy(cnt).to(dev)}
-    a, lp, z = actor.act(torch.from_numpy(obs).to(dev), g, seed=77, step=3, row_offset=1000, want_logits=True)
+    a, lp, z, v = actor.act(torch.from_numpy(obs).to(dev), g, seed=77, step=3, row_offset=1000, want_logits=True,
+                            want_values=True)
+    np.testing.assert_allclose(v.cpu().numpy(), P.values(w, obs, feat, cnt), rtol=1e-4, atol=2e-5)
+    a_only, lp_only = actor.act(torch.from_numpy(obs).to(dev), g, seed=77, step=3, row_offset=1000)
+    assert torch.equal(a_only, a) and torch.equal(lp_only, lp)          # the actor-only instance agrees
+    # garbage (NaN) in the padded rows must not reach any output
+    junk = feat.copy()
+    junk[np.arange(K)[None, :] >= cnt[:, None]] = np.nan
+    aj, lpj = actor.act(torch.from_numpy(obs).to(dev), {"nbr_feat": torch.from_numpy(junk).to(dev),
+                                                        "nbr_cnt": g["nbr_cnt"]}, seed=77, step=3, row_offset=1000)
+    assert torch.equal(aj, a) and torch.equal(lpj, lp)
     a0, lp0, z0, margin = P.act(w, obs, feat, cnt, seed=77, step=3, row_offset=1000)
     # fp32 production tolerance (north_star: 1e-4 relative)
     np.testing.assert_allclose(z.cpu().numpy(), z0, rtol=1e-4, atol=2e-5)
@@ -142,8 +158,9 @@ def test_gsm_collect_equals_stepwise_collect(scn, N):
             t_box = [0]
 
             def policy(obs, graph):
-                a, lp = actor.act(obs, graph, seed=21, step=100 + t_box[0], row_offset=40 * N)
+                a, lp, v = actor.act(obs, graph, seed=21, step=100 + t_box[0], row_offset=40 * N, want_values=True)
                 buf["logp"][t_box[0]].copy_(lp)
+                buf["values"][t_box[0]].copy_(v)
                 t_box[0] += 1
                 return a
             collect(env, policy, buf)
@@ -151,7 +168,7 @@ def test_gsm_collect_equals_stepwise_collect(scn, N):
             collect_fused(env, actor, buf, seed=21, first_step=100)
         else:
             g = collect_fused(env, actor, buf, seed=21, first_step=100, graph=True)
-            for k in ("actions", "reward", "logp"):
+            for k in ("actions", "reward", "logp", "values"):
                 buf[k].zero_()
             g.replay()
         torch.cuda.synchronize()
@@ -182,7 +199,7 @@ def test_collect_fused_over_stream_shards_equals_one_handle(graph):
         buf.reset_env()
         r = collect_fused(env, actor, buf, seed=3, first_step=50, graph=graph)
         if graph:
-            buf["actions"].zero_(); buf["logp"].zero_()
+            buf["actions"].zero_(); buf["logp"].zero_(); buf["values"].zero_()
             r.replay()
         torch.cuda.synchronize()
         outs.append({k: v.clone() for k, v in buf.data.items()})
