@@ -103,6 +103,8 @@ SYMBOLS = {
     "gsm_observe": (C.c_int, [_H, _IO, C.c_void_p]),
     "gsm_set_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_get_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gsm_set_episode": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    "gsm_get_episode": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "gsm_host_io": (C.c_int, [_H, _IO]),
     "gsm_reset_host": (C.c_int, [_H, C.c_uint64, C.c_void_p, C.c_int64, _IO]),
     "gsm_step_host": (C.c_int, [_H, _IO]),
@@ -114,6 +116,8 @@ SYMBOLS = {
                           C.c_void_p]),
     "gsm_policy_act": (C.c_int, [C.POINTER(GsmPolicyWeights), C.POINTER(GsmPolicyIO), C.c_int, C.c_void_p]),
     "gsm_policy_last_error": (C.c_char_p, []),
+    "gsm_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
+                          C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gsm_collect": (C.c_int, [_H, C.POINTER(GsmPolicyWeights), C.c_int32, _IO, C.c_void_p, C.c_void_p,
                               C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]),
 }

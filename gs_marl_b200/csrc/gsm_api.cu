@@ -530,6 +530,20 @@ int gsm_get_state(gsm_env* h, void* agent_state, void* landmark_pos, int32_t* st
   return GSM_OK;
 }
 
+int gsm_set_episode(gsm_env* h, const int32_t* episode, void* stream) {
+  if (!h) return GSM_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  if (episode) GSM_CUDA(h, cudaMemcpyAsync(h->hp.episode, episode, h->sz.step_count, cudaMemcpyDefault, (cudaStream_t)stream));
+  return GSM_OK;
+}
+
+int gsm_get_episode(gsm_env* h, int32_t* episode, void* stream) {
+  if (!h) return GSM_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  if (episode) GSM_CUDA(h, cudaMemcpyAsync(episode, h->hp.episode, h->sz.step_count, cudaMemcpyDefault, (cudaStream_t)stream));
+  return GSM_OK;
+}
+
 int gsm_host_io(gsm_env* h, gsm_step_io* out) {
   if (!h || !out) return GSM_ERR_INVALID_ARG;
   DeviceGuard guard(h->device);
@@ -613,6 +627,7 @@ int gsm_collect(gsm_env* h, const gsm_policy_weights* w, int32_t n_steps, const 
     return fail(h, GSM_ERR_INVALID_ARG, "gsm_collect: weights.n_actions != cfg.n_discrete_actions");
   if (!io->actions || !io->obs || !io->nbr_feat || !io->nbr_cnt)
     return fail(h, GSM_ERR_INVALID_ARG, "gsm_collect needs io.actions, io.obs, io.nbr_feat and io.nbr_cnt");
+  if (h->auto_reset && !io->done) return fail(h, GSM_ERR_INVALID_ARG, "auto-reset collect needs io.done");
   DeviceGuard guard(h->device);
   const int64_t rows = h->hp.n_envs * h->hp.N;
   const int64_t slot_rows = (h->slot_envs ? h->slot_envs : h->hp.n_envs) * h->hp.N;
@@ -641,6 +656,10 @@ int gsm_collect(gsm_env* h, const gsm_policy_weights* w, int32_t n_steps, const 
     h->launches += 1;
     st = do_step(h, cur, (cudaStream_t)stream);
     if (st) return st;
+    if (h->auto_reset) {   // the vec-env wrapper's reset-on-done: finished envs get their first observation in slot t+1
+      st = gsm_reset(h, h->seed, cur.done, h->hp.N, &cur, stream);
+      if (st) return st;
+    }
   }
   return GSM_OK;
 }

@@ -209,6 +209,37 @@ graph_actor_kernel(const __grid_constant__ PolicyParams w, const __grid_constant
   }
 }
 
+// ---- buffer.compute_returns / compute_cost_returns (utils/graph_separated_buffer.py, SOURCES.txt:33;
+// withheld — the on-policy lineage's GAE recursion, [DECL] SPEC.md §11): one thread per (row, head),
+// backward scan over the T slots; consecutive threads touch consecutive addresses in every slot.
+struct GaeParams {
+  const float* reward; const float* cost; const float* values; const uint8_t* done;
+  float* returns; float* adv;
+  int64_t n_rows, slot_rows;
+  int T;
+  float gamma, lam;
+};
+__global__ void __launch_bounds__(256) gae_kernel(const __grid_constant__ GaeParams p) {
+  constexpr int V = GSM_POLICY_VALUE_HEADS;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= p.n_rows * V) return;
+  const int64_t row = g / V;
+  const int head = (int)(g - row * V);
+  const float* rw = head == 0 ? p.reward : p.cost;
+  float gae = 0.f;
+  float v_next = p.values[((int64_t)p.T * p.slot_rows + row) * V + head];
+  for (int t = p.T - 1; t >= 0; t--) {
+    const int64_t o = (int64_t)t * p.slot_rows + row;
+    const float mask = p.done[o] ? 0.f : 1.f;      // done at step t: slot t+1 starts a new episode
+    const float v = p.values[o * V + head];
+    const float delta = rw[o] + p.gamma * v_next * mask - v;
+    gae = delta + p.gamma * p.lam * mask * gae;
+    if (p.adv) p.adv[o * V + head] = gae;
+    p.returns[o * V + head] = gae + v;
+    v_next = v;
+  }
+}
+
 static int launch_actor(const PolicyParams& w, const PolicyIO& io, int n_actions, cudaStream_t st) {
   if (io.n_rows == 0) return 0;
   const int block = 128;            // the kernel's counting sort assumes exactly 128
@@ -280,6 +311,27 @@ int gsm_policy_act(const gsm_policy_weights* w, const gsm_policy_io* io, int dev
   k.K = io->max_nbrs; k.greedy = io->greedy;
   const int e = gsm::launch_actor(p, k, w->n_actions, (cudaStream_t)stream);
   if (e) return pfail(GSM_ERR_CUDA, cudaGetErrorString((cudaError_t)e));
+  return GSM_OK;
+}
+
+int gsm_gae(const float* reward, const float* cost, const float* values, const uint8_t* done, int32_t n_steps,
+            int64_t n_rows, int64_t slot_rows, float gamma, float lam, float* returns, float* advantages,
+            int device, void* stream) {
+  if (!reward || !cost || !values || !done || !returns)
+    return pfail(GSM_ERR_INVALID_ARG, "gsm_gae: reward, cost, values, done and returns are required");
+  if (n_steps < 1 || n_rows < 0 || slot_rows < n_rows) return pfail(GSM_ERR_INVALID_ARG, "gsm_gae: bad sizes");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return pfail(GSM_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  }
+  if (n_rows == 0) return GSM_OK;
+  DevGuard guard(device);
+  gsm::GaeParams p{reward, cost, values, done, returns, advantages, n_rows, slot_rows, n_steps, gamma, lam};
+  const int64_t threads = n_rows * GSM_POLICY_VALUE_HEADS;
+  gsm::gae_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return pfail(GSM_ERR_CUDA, cudaGetErrorString(e));
   return GSM_OK;
 }
 

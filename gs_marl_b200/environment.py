@@ -190,6 +190,21 @@ class MultiAgentGraphConstrainEnv:
                                                t.data_ptr(), self._stream()))
         return a, l, t
 
+    def get_episode(self) -> torch.Tensor:
+        """Episode counter per env (keys the reset draws; part of a full checkpoint)."""
+        ep = torch.zeros((self.n_envs,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.gsm_get_episode(self._h, ep.data_ptr(), self._stream()))
+        return ep
+
+    def set_episode(self, episode):
+        ep = torch.as_tensor(episode).to(device=self.device, dtype=torch.int32).contiguous()
+        if tuple(ep.shape) != (self.n_envs,):
+            raise ValueError(f"episode must have shape ({self.n_envs},)")
+        with torch.cuda.device(self.device):
+            self._check(self.lib.gsm_set_episode(self._h, ep.data_ptr(), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+
     @property
     def kernel_launches(self) -> int:
         return int(self.lib.gsm_kernel_launches(self._h))
@@ -337,6 +352,13 @@ class StreamShardedEnv:
     def get_state(self):
         parts = [sh.get_state() for sh in self.shards]
         return tuple(torch.cat([p[j] for p in parts], 0) for j in range(3))
+
+    def get_episode(self):
+        return torch.cat([sh.get_episode() for sh in self.shards], 0)
+
+    def set_episode(self, episode):
+        for sh, (lo, hi) in zip(self.shards, self.bounds):
+            sh.set_episode(episode[lo:hi])
 
     def set_state(self, agent_state=None, landmark_pos=None, step_count=None):
         for sh, (lo, hi) in zip(self.shards, self.bounds):

@@ -94,6 +94,25 @@ class GraphRolloutBuffer:
             sh.lib.gsm_reset(sh._h, sh._seed, None, 1, C.byref(self._io_reset[j]), st)))
         self.step = 0
 
+    def compute_returns(self, gamma: float = 0.99, gae_lambda: float = 0.95):
+        """buffer.compute_returns + compute_cost_returns of the lineage (GAE, SPEC.md §11), one kernel
+        for both critics: fills `returns` and `advantages` [T, n_envs, N, 2] from reward / cost / done
+        and `values` (slot T must hold the bootstrap prediction for the last observation)."""
+        d, e = self.data, self.env
+        for k in ("returns", "advantages"):
+            if k not in d:
+                d[k] = torch.zeros_like(d["values"][:-1])
+        lib = abi.load_library()
+        rows = d["reward"][0].numel()
+        with torch.cuda.device(e.device):
+            st = lib.gsm_gae(d["reward"].data_ptr(), d["cost"].data_ptr(), d["values"].data_ptr(),
+                             d["done"].data_ptr(), self.T, rows, rows, float(gamma), float(gae_lambda),
+                             d["returns"].data_ptr(), d["advantages"].data_ptr(), e.device.index or 0,
+                             C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream))
+        if st != 0:
+            raise abi.GsmError(f"{lib.gsm_status_string(st).decode()}: {lib.gsm_policy_last_error().decode()}")
+        return d["returns"], d["advantages"]
+
     def after_update(self):
         """Lineage buffers copy the last observation to slot 0 after an update."""
         for k in _OBS_KEYS:
@@ -112,6 +131,9 @@ def collect(env: MultiAgentGraphConstrainEnv, policy: Callable, buf: GraphRollou
             a = policy(buf.data["obs"][t], buf.graph(t))
             buf.data["actions"][t].copy_(a)
             env._check(env.lib.gsm_step(env._h, C.byref(buf._io[t]), stream))
+            if env.auto_reset:      # finished envs restart; their first observation replaces slot t+1
+                env._check(env.lib.gsm_reset(env._h, env._seed, C.c_void_p(buf.data["done"][t].data_ptr()),
+                                             env.world.n_agents, C.byref(buf._io[t]), stream))
     buf.step = buf.T
     return buf
 
@@ -130,6 +152,8 @@ def collect_fused(env: MultiAgentGraphConstrainEnv, actor, buf: GraphRolloutBuff
     capture: re-capture after an optimizer step)."""
     w = actor.packed()
     logp, values = buf.data["logp"], buf.data["values"]
+    for sh in buf._shards:          # reset-on-done inside the loop follows the env's flag
+        sh._check(sh.lib.gsm_set_auto_reset(sh._h, int(bool(env.auto_reset))))
 
     def enqueue():
         buf._on_shards(lambda sh, j, st: sh._check(sh.lib.gsm_collect(
@@ -144,9 +168,10 @@ def collect_fused(env: MultiAgentGraphConstrainEnv, actor, buf: GraphRolloutBuff
             return buf
         # one eager rollout first (module load / first-launch work must not happen inside a
         # capture); the env state is put back afterwards, slot 0 is never written by a collect
-        saved = env.get_state()
+        saved, saved_ep = env.get_state(), env.get_episode()
         enqueue()
         env.set_state(*saved)
+        env.set_episode(saved_ep)          # re-draws inside the replay must see the same episode numbers
         torch.cuda.synchronize(env.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

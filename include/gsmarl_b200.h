@@ -206,6 +206,12 @@ int gsm_set_state(gsm_env* h, const void* agent_state, const void* landmark_pos,
 int gsm_get_state(gsm_env* h, void* agent_state, void* landmark_pos, int32_t* step_count,
                   void* stream);
 
+/* Episode counters (device int32 [n_envs]; NULL = skip): the reset draws are keyed by (seed, global
+ * env index, episode), so a checkpoint that restores agent_state / landmark_pos / step_count must
+ * restore these too for the NEXT re-draws to repeat. */
+int gsm_set_episode(gsm_env* h, const int32_t* episode, void* stream);
+int gsm_get_episode(gsm_env* h, int32_t* episode, void* stream);
+
 /* Host-buffer variants: every pointer in io / arguments is HOST memory.  The call
  * stages through pinned memory, copies H2D, runs the device path on the handle's own
  * stream, copies D2H and synchronises — this is the numpy-facing drop-in path the
@@ -288,11 +294,25 @@ const char* gsm_policy_last_error(void);
  * reads observation slot t and writes actions (and logp) slot t with Philox step first_step + t;
  * gsm_step writes reward / cost / done slot t and the next observation into slot t + 1 — the
  * buffer "insert" is where the kernels write.  Slot strides follow gsm_get_io_sizes /
- * gsm_set_slot_envs.  Needs a GSM_F32, GSM_ACT_DISCRETE handle with n_discrete_actions ==
+ * gsm_set_slot_envs.  With gsm_set_auto_reset enabled, envs that finish at step t keep their terminal
+ * reward / cost / done in slot t and are re-drawn, their first observation replacing slot t + 1.
+ * Needs a GSM_F32, GSM_ACT_DISCRETE handle with n_discrete_actions ==
  * w->n_actions. */
 int gsm_collect(gsm_env* h, const gsm_policy_weights* w, int32_t n_steps, const gsm_step_io* io,
                 float* logp, float* values, uint64_t seed, uint64_t first_step, int32_t greedy,
                 void* stream);
+
+/* buffer.compute_returns + compute_cost_returns (utils/graph_separated_buffer.py, SOURCES.txt:33;
+ * withheld: the on-policy lineage's GAE recursion, declared in SPEC.md §11) for both critics in one
+ * launch.  DEVICE pointers over the rollout buffer's slots, slot stride = slot_rows rows:
+ * reward, cost: float [T][slot_rows]; done: u8 [T][slot_rows]; values: float [T+1][slot_rows][2]
+ * (slot T = bootstrap prediction for the last observation); returns, advantages (may be NULL):
+ * float [T][slot_rows][2].  For t = T-1..0, head h (0: reward, 1: cost):
+ *   mask = done[t] ? 0 : 1;  delta = r_h[t] + gamma * V_h[t+1] * mask - V_h[t];
+ *   gae = delta + gamma * lam * mask * gae;  advantages[t] = gae;  returns[t] = gae + V_h[t]. */
+int gsm_gae(const float* reward, const float* cost, const float* values, const uint8_t* done,
+            int32_t n_steps, int64_t n_rows, int64_t slot_rows, float gamma, float lam,
+            float* returns, float* advantages, int device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -93,3 +93,18 @@ def act(w, obs, nbr_feat, nbr_cnt, seed=0, step=0, row_offset=0, greedy=False, d
     zm = z.max(1, keepdims=True)
     lse = zm[:, 0] + np.log(np.exp(z - zm).sum(1))
     return a, z[np.arange(z.shape[0]), a] - lse, z, margin
+
+
+def gae(reward, cost, values, done, gamma, lam, dtype=np.float64):
+    """SPEC.md §11.  reward, cost, done [T, R]; values [T+1, R, 2] -> returns, advantages [T, R, 2]."""
+    rw = np.stack([np.asarray(reward, dtype), np.asarray(cost, dtype)], -1)
+    v = np.asarray(values, dtype)
+    mask = (1.0 - (np.asarray(done) != 0).astype(dtype))[..., None]
+    T = rw.shape[0]
+    ret, adv = np.zeros_like(rw), np.zeros_like(rw)
+    g = np.zeros_like(rw[0])
+    for t in range(T - 1, -1, -1):
+        delta = rw[t] + gamma * v[t + 1] * mask[t] - v[t]
+        g = delta + gamma * lam * mask[t] * g
+        adv[t], ret[t] = g, g + v[t]
+    return ret, adv

@@ -837,3 +837,34 @@ def test_slot_envs_argument_checks():
     assert env.lib.gsm_set_slot_envs(env._h, 8) == 0 and env.lib.gsm_set_slot_envs(env._h, 0) == 0
     assert env.lib.gsm_set_slot_envs(None, 8) == -1
     env.close()
+
+
+def test_checkpoint_resume_with_episode_counters():
+    """A checkpoint = agent_state + landmark_pos + step_count + EPISODE counters: restored into a fresh
+    handle, the following steps — including the re-draws of envs that finish — repeat bit for bit.
+    Without the episode counters the re-draws would come from episode 1 again."""
+    cfg = make_cfg("navigation", 3, "f32").replace(episode_length=4)
+    a = _env(cfg, 200, seed=6, env_offset=11, auto_reset=True)
+    a.reset()
+    rng = np.random.default_rng(100)
+    acts = [torch.from_numpy(random_actions(cfg, rng, (200,))).cuda() for s in range(14)]
+    for s in range(6):                                   # one re-draw behind us, t = 2 inside episode 2
+        a.step(acts[s])
+    state, ep = a.get_state(), a.get_episode()
+    assert int(ep.min()) == int(ep.max()) == 2
+    b = _env(cfg, 200, seed=6, env_offset=11, auto_reset=True)
+    b.set_state(*state)
+    b.set_episode(ep)
+    for s in range(6, 14):                               # two more re-draws
+        ra, rb = a.step(acts[s]), b.step(acts[s])
+    torch.cuda.synchronize()
+    for k in OUT_KEYS:
+        assert torch.equal(a.buf[k], b.buf[k]), k
+    c = _env(cfg, 200, seed=6, env_offset=11, auto_reset=True)      # the same WITHOUT the counters diverges
+    c.set_state(*state)
+    for s in range(6, 14):
+        c.step(acts[s])
+    torch.cuda.synchronize()
+    assert not torch.equal(a.buf["obs"], c.buf["obs"])
+    for e in (a, b, c):
+        e.close()

@@ -146,12 +146,12 @@ def test_gsm_collect_equals_stepwise_collect(scn, N):
     collect loop calling the same kernels one step at a time: bit-exact buffers."""
     from gs_marl_b200.environment import MultiAgentGraphConstrainEnv
     from gs_marl_b200.rollout import GraphRolloutBuffer, collect, collect_fused
-    cfg = make_cfg(scn, N, "f32")
+    cfg = make_cfg(scn, N, "f32").replace(episode_length=3)     # episodes end (and restart) inside the rollout
     actor = GraphAttentionActor(len(cfg.discrete_u), seed=12)
     T, n_envs = 7, 300
     bufs = []
     for mode in ("python", "fused", "graph"):
-        env = MultiAgentGraphConstrainEnv(cfg, n_envs, env_offset=40, seed=5)
+        env = MultiAgentGraphConstrainEnv(cfg, n_envs, env_offset=40, seed=5, auto_reset=True)
         buf = GraphRolloutBuffer(env, T)
         buf.reset_env()
         if mode == "python":
@@ -178,6 +178,8 @@ def test_gsm_collect_equals_stepwise_collect(scn, N):
         assert torch.equal(bufs[0][k], bufs[1][k]), k
         assert torch.equal(bufs[0][k], bufs[2][k]), k
     assert bufs[0]["actions"].float().std() > 0
+    d = bufs[0]["done"].cpu().numpy()
+    assert d[2].all() and d[5].all() and not d[[0, 1, 3, 4, 6]].any()      # done every 3rd step: envs restarted
 
 
 @pytest.mark.gpu
@@ -206,3 +208,44 @@ def test_collect_fused_over_stream_shards_equals_one_handle(graph):
         env.close()
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+def test_gae_oracle_closed_form():
+    """gamma = lam = 1, no dones: returns[t] = sum of the rewards from t on + V[T]."""
+    rng = np.random.default_rng(0)
+    T, R = 9, 5
+    rw, cs = rng.standard_normal((T, R)), rng.random((T, R))
+    v = rng.standard_normal((T + 1, R, 2))
+    ret, adv = P.gae(rw, cs, v, np.zeros((T, R), np.uint8), 1.0, 1.0)
+    np.testing.assert_allclose(ret[..., 0], np.cumsum(rw[::-1], 0)[::-1] + v[T, :, 0], atol=1e-12)
+    np.testing.assert_allclose(ret[..., 1], np.cumsum(cs[::-1], 0)[::-1] + v[T, :, 1], atol=1e-12)
+    np.testing.assert_allclose(adv, ret - v[:-1], atol=1e-12)
+    # a done cuts the bootstrap and the accumulation
+    d = np.zeros((T, R), np.uint8); d[4] = 1
+    ret2, _ = P.gae(rw, cs, v, d, 1.0, 1.0)
+    np.testing.assert_allclose(ret2[4, :, 0], rw[4], atol=1e-12)
+    np.testing.assert_allclose(ret2[:4], P.gae(rw[:5], cs[:5], v[:6], d[:5], 1.0, 1.0)[0][:4], atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gae_kernel_matches_oracle_on_a_collected_rollout():
+    from gs_marl_b200.environment import MultiAgentGraphConstrainEnv
+    from gs_marl_b200.rollout import GraphRolloutBuffer, collect_fused
+    cfg = make_cfg("navigation", 3, "f32").replace(episode_length=5)
+    actor = GraphAttentionActor(len(cfg.discrete_u), seed=14)
+    env = MultiAgentGraphConstrainEnv(cfg, 777, seed=2)
+    T = 12                                               # episodes end inside the rollout: done flags set
+    buf = GraphRolloutBuffer(env, T)
+    buf.reset_env()
+    collect_fused(env, actor, buf, seed=1)
+    *_, vT = actor.act(buf["obs"][T], buf.graph(T), want_values=True)
+    buf["values"][T].copy_(vT)
+    ret, adv = buf.compute_returns(0.97, 0.9)
+    torch.cuda.synchronize()
+    done = buf["done"].cpu().numpy()
+    assert done.any() and not done.all()
+    r0, a0 = P.gae(buf["reward"].cpu().numpy().reshape(T, -1), buf["cost"].cpu().numpy().reshape(T, -1),
+                   buf["values"].cpu().numpy().reshape(T + 1, -1, 2), done.reshape(T, -1), 0.97, 0.9)
+    np.testing.assert_allclose(ret.cpu().numpy().reshape(T, -1, 2), r0, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(adv.cpu().numpy().reshape(T, -1, 2), a0, rtol=1e-4, atol=1e-4)
+    env.close()
