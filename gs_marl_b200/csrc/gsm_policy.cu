@@ -11,15 +11,18 @@
 //   z   = W_h [e ; sum_r a_r m_r] + b_h                     [n_actions] logits
 //   action = argmax_k (z_k + Gumbel_k),  Gumbel from Philox4x32-10 keyed like the env resets.
 //
-// Design for sm_100a: one thread per agent row, no shared memory, no shuffles.  The weights ride
-// in the kernel PARAMETER space (8.5 KB, __grid_constant__), so every weight is a constant-bank
-// operand of an FFMA (`FFMA R, R, c[0x0][imm], R`): the 64-wide hidden loops are fully unrolled
-// and issue no load instructions for weights at all.  The head is linear, so W_h's neighbour half
-// is applied to every row's m_r on the fly (hr = W_h[:, H:] m_r) and the softmax is the online
-// (running max / running sum) form over 1 + n_actions accumulators: a row costs 64 x 13 FFMA-class
-// instructions and nothing of size H is ever stored.  Only the cnt valid rows are visited; the
-// padded rows the env kernel zero-fills are never read.  Bound: fp32 issue (not HBM: 220 B per
-// agent in, 8 B out).
+// Design for sm_100a: one thread per agent row, no shuffles, shared memory only for the 128-entry
+// sort below.  The weights ride in the kernel PARAMETER space (9.5 KB, __grid_constant__): the
+// 64-wide hidden loops are fully unrolled, so every weight has an immediate constant-bank offset,
+// ptxas fetches four at a time with LDCU.128 into uniform registers and the FFMAs take them as
+// uniform-register operands — no weight ever goes through a load/store unit.  (Partially unrolled
+// loops with a uniform-register INDEX into the constant bank measured 4x slower; packed FFMA2
+// variants did not pay either: profiles/README.md, profiles/fma_peak.cu.)  The head is linear, so
+// W_h's neighbour half is applied to every row's m_r on the fly (hr = W_h[:, H:] m_r) and the
+// softmax is the online (running max / running sum) form over 1 + n_actions accumulators: a row
+// costs 64 x 13 FFMA-class instructions and nothing of size H is ever stored.  Only the cnt valid
+// rows are visited; the padded rows the env kernel zero-fills are never read.  Bound: fp32 issue
+// slots (17.25 per 13 FFMA; 88.7 % issue-active at 786k rows), not HBM (220 B per agent in, 8 B out).
 #include <cuda_runtime.h>
 
 #include <cstdint>
