@@ -68,98 +68,147 @@ __device__ __forceinline__ void philox_p(uint32_t c0, uint32_t c1, uint32_t c2, 
 
 // NV = 0: actor only; NV = GSM_POLICY_VALUE_HEADS: the critics ride along as NV more rows of the head
 // (+2 FFMA per hidden unit and row), for collect loops that store value predictions.
+//
+// Work decomposition ("flattened rows").  A block owns 128 consecutive agents.  Phase 1: thread a
+// runs agent a's ego branch.  Phase 2: the block's valid neighbour rows — sum(cnt) of them, found
+// through an exclusive prefix of cnt — are one flat list of independent work items; thread t takes
+// items t, t+128, ... (agent by binary search in the prefix, 7 steps), computes that row's attention
+// score and head contribution and parks the 1 + NZ floats in shared memory.  Phase 3: thread a folds
+// its own agent's rows, in row order, into the online softmax.  Every lane of every warp carries a
+// real row in phase 2 whatever the per-agent counts are, and a 49 152-agent batch becomes ~250 000
+// threads' worth of items instead of 49 152 threads of very different length — the thread-per-agent
+// version had 20.8 (28.1 after a per-block counting sort by cnt) of 32 lanes active and 10 warps/SM.
+// Row items are processed in chunks of CH so that shared memory does not depend on K.
+__device__ __forceinline__ float2 bc(float w) { return make_float2(w, w); }
+
 template <int NA, int NV>
 __global__ void __launch_bounds__(128)
 graph_actor_kernel(const __grid_constant__ PolicyParams w, const __grid_constant__ PolicyIO io) {
-  // The row loop runs cnt times and cnt differs from agent to agent (0..K): a warp would pay for
-  // its busiest lane (measured: 20.8 of 32 lanes active per instruction).  So the block first
-  // counting-sorts its 128 agents by cnt, busiest first, and thread t serves the t-th agent of
-  // that order: lanes of one warp then loop (almost) equally long.  Outputs are per agent, so the
-  // order inside a bin does not matter.
-  __shared__ int s_bin[34];
-  __shared__ int s_perm[128];
-  const int tid = threadIdx.x;
-  const int64_t base = (int64_t)blockIdx.x * 128;
-  if (tid < 34) s_bin[tid] = 0;
-  __syncthreads();
-  int my_cnt = -1, my_bin = 33, my_rank = 0;
-  if (base + tid < io.n_rows) {
-    my_cnt = io.nbr_cnt[base + tid];
-    my_cnt = my_cnt < 0 ? 0 : (my_cnt > io.K ? io.K : my_cnt);
-    my_bin = 32 - (my_cnt > 32 ? 32 : my_cnt);
-    my_rank = atomicAdd(&s_bin[my_bin], 1);
-  }
-  s_perm[tid] = -1;
-  __syncthreads();
-  if (tid < 32) {                       // exclusive scan of the 33 bins by warp 0
-    const int v = s_bin[tid];
-    int x = v;
+  constexpr int NZ = NA + NV, AG = 128, RS = NZ + 1, CH = RS <= 10 ? 1024 : 512;   // static smem <= 48 KB
+  __shared__ int s_pre[AG + 1];
+  __shared__ int s_wtot[4];
+  __shared__ float s_row[CH * RS];
+  __shared__ float s_z[AG * NZ];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t base = (int64_t)blockIdx.x * AG;
+  const int64_t i = base + tid;
+  const bool valid = i < io.n_rows;
+  int cnt = 0;
+  if (valid) { cnt = io.nbr_cnt[i]; cnt = cnt < 0 ? 0 : (cnt > io.K ? io.K : cnt); }
+  {  // exclusive prefix of cnt over the block
+    int x = cnt;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(~0u, x, d); if (tid >= d) x += y; }
-    const int tot = __shfl_sync(~0u, x, 31);
-    __syncwarp();
-    s_bin[tid] = x - v;
-    if (tid == 0) s_bin[32] = tot;      // bin 32 (cnt == 0) starts after bins 0..31
-  }
-  __syncthreads();
-  if (my_cnt >= 0) s_perm[s_bin[my_bin] + my_rank] = tid | (my_cnt << 8);
-  __syncthreads();
-  const int slot = s_perm[tid];
-  if (slot < 0) return;
-  const int64_t i = base + (slot & 0xff);
-  const int cnt = slot >> 8;
-
-  constexpr int NZ = NA + NV;
-  float z[NZ];
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(~0u, x, d); if (lane >= d) x += y; }
+    if (lane == 31) s_wtot[warp] = x;
+    __syncthreads();
+    int off = 0;
 #pragma unroll
-  for (int a = 0; a < NZ; a++) z[a] = w.head_b[a];
+    for (int k = 0; k < 4; k++) off += k < warp ? s_wtot[k] : 0;
+    s_pre[tid] = off + x - cnt;
+    if (tid == AG - 1) s_pre[AG] = off + x;
+  }
 
-  {  // ego branch
-    const float2* o2 = reinterpret_cast<const float2*>(io.obs + i * GSM_OBS_DIM);
-    const float2 o01 = o2[0], o23 = o2[1], o45 = o2[2];
+  // phase 1: ego branch, agents (t, t + 64) packed into one thread of warps 0-1 (FFMA2, as below);
+  // warps 2-3 go straight to the barrier and leave their issue slots to other blocks
+  if (tid < AG / 2 && valid) {
+    const int64_t iB = i + AG / 2 < io.n_rows ? i + AG / 2 : i;
+    const float* oA = io.obs + i * GSM_OBS_DIM;
+    const float* oB = io.obs + iB * GSM_OBS_DIM;
+    const float2 d0 = make_float2(oA[0], oB[0]), d1 = make_float2(oA[1], oB[1]), d2 = make_float2(oA[2], oB[2]),
+                 d3 = make_float2(oA[3], oB[3]), d4 = make_float2(oA[4], oB[4]), d5 = make_float2(oA[5], oB[5]);
+    float2 z2[NZ];
+#pragma unroll
+    for (int a = 0; a < NZ; a++) z2[a] = bc(w.head_b[a]);
 #pragma unroll
     for (int j = 0; j < H; j++) {
-      float e = w.ego_b[j];
-      e = fmaf(w.ego_w[j][0], o01.x, e); e = fmaf(w.ego_w[j][1], o01.y, e);
-      e = fmaf(w.ego_w[j][2], o23.x, e); e = fmaf(w.ego_w[j][3], o23.y, e);
-      e = fmaf(w.ego_w[j][4], o45.x, e); e = fmaf(w.ego_w[j][5], o45.y, e);
-      e = fmaxf(e, 0.f);
+      float2 e = bc(w.ego_b[j]);
+      e = __ffma2_rn(bc(w.ego_w[j][0]), d0, e); e = __ffma2_rn(bc(w.ego_w[j][1]), d1, e);
+      e = __ffma2_rn(bc(w.ego_w[j][2]), d2, e); e = __ffma2_rn(bc(w.ego_w[j][3]), d3, e);
+      e = __ffma2_rn(bc(w.ego_w[j][4]), d4, e); e = __ffma2_rn(bc(w.ego_w[j][5]), d5, e);
+      e.x = fmaxf(e.x, 0.f); e.y = fmaxf(e.y, 0.f);
 #pragma unroll
-      for (int a = 0; a < NZ; a++) z[a] = fmaf(w.head_w[a][j], e, z[a]);
+      for (int a = 0; a < NZ; a++) z2[a] = __ffma2_rn(bc(w.head_w[a][j]), e, z2[a]);
     }
+#pragma unroll
+    for (int a = 0; a < NZ; a++) { s_z[tid * NZ + a] = z2[a].x; s_z[(tid + AG / 2) * NZ + a] = z2[a].y; }
   }
+  __syncthreads();                      // s_pre complete
+  const int total = s_pre[AG];
+  const int my0 = s_pre[tid], my1 = my0 + cnt;
+  float z[NZ];
+#pragma unroll
+  for (int a = 0; a < NZ; a++) z[a] = s_z[tid * NZ + a];       // garbage for !valid threads, never used
 
-  // neighbour rows: online softmax over the attention score, W_h's second half applied per row
+  // online softmax state of MY agent over its rows, in row order
   float mx = -__int_as_float(0x7f800000), s = 0.f, acc[NZ];
 #pragma unroll
   for (int a = 0; a < NZ; a++) acc[a] = 0.f;
-  const float2* f2 = reinterpret_cast<const float2*>(io.nbr_feat + i * (int64_t)io.K * GSM_NBR_FEAT_DIM);
-  float2 n01, n23, n45;                 // next row, loaded one iteration ahead
-  if (cnt > 0) { n01 = f2[0]; n23 = f2[1]; n45 = f2[2]; }
-  for (int r = 0; r < cnt; r++) {
-    const float2 f01 = n01, f23 = n23, f45 = n45;
-    if (r + 1 < cnt) { n01 = f2[3 * r + 3]; n23 = f2[3 * r + 4]; n45 = f2[3 * r + 5]; }
-    float t = w.att_b, hr[NZ];
+  const float* ffeat = io.nbr_feat + base * (int64_t)io.K * GSM_NBR_FEAT_DIM;
+
+  for (int c0 = 0; c0 < total; c0 += CH) {          // block-uniform trip count
+    const int cend = total < c0 + CH ? total : c0 + CH;
+    // phase 2: TWO neighbour rows per thread (items q and q + AG), packed into the halves of float2
+    // registers for Blackwell's packed fp32 FMA (FFMA2, `fma.rn.f32x2`) with the weight as the
+    // broadcast uniform scalar operand — full FMA rate at half the issue slots of scalar FFMA
+    // (profiles/fma_peak.cu).  Items are homogeneous, so the pairing costs no divergence; an odd
+    // tail duplicates its row into the second half and stores it once.
+    for (int q = c0 + tid; q < cend; q += 2 * AG) {
+      const int q1 = q + AG < cend ? q + AG : q;
+      int lo0 = 0, hi0 = AG, lo1 = 0, hi1 = AG;     // largest a with s_pre[a] <= q
 #pragma unroll
-    for (int a = 0; a < NZ; a++) hr[a] = 0.f;
+      for (int it = 0; it < 7; it++) {
+        const int m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
+        if (s_pre[m0] <= q) lo0 = m0; else hi0 = m0;
+        if (s_pre[m1] <= q1) lo1 = m1; else hi1 = m1;
+      }
+      // scalar loads on purpose: a 64-bit load pins (x, y) of ONE row to an aligned register pair and
+      // ptxas then re-assembles every (row 0, row 1) operand pair with two MOVs per FFMA2
+      const float* g0 = ffeat + ((int64_t)lo0 * io.K + (q - s_pre[lo0])) * GSM_NBR_FEAT_DIM;
+      const float* g1 = ffeat + ((int64_t)lo1 * io.K + (q1 - s_pre[lo1])) * GSM_NBR_FEAT_DIM;
+      const float2 d0 = make_float2(g0[0], g1[0]), d1 = make_float2(g0[1], g1[1]), d2 = make_float2(g0[2], g1[2]),
+                   d3 = make_float2(g0[3], g1[3]), d4 = make_float2(g0[4], g1[4]), d5 = make_float2(g0[5], g1[5]);
+      float2 t2 = bc(w.att_b), hr[NZ];
 #pragma unroll
-    for (int j = 0; j < H; j++) {
-      float m = w.nbr_b[j];
-      m = fmaf(w.nbr_w[j][0], f01.x, m); m = fmaf(w.nbr_w[j][1], f01.y, m);
-      m = fmaf(w.nbr_w[j][2], f23.x, m); m = fmaf(w.nbr_w[j][3], f23.y, m);
-      m = fmaf(w.nbr_w[j][4], f45.x, m); m = fmaf(w.nbr_w[j][5], f45.y, m);
-      m = fmaxf(m, 0.f);
-      t = fmaf(w.att_w[j], m, t);
+      for (int a = 0; a < NZ; a++) hr[a] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int a = 0; a < NZ; a++) hr[a] = fmaf(w.head_w[a][H + j], m, hr[a]);
+      for (int j = 0; j < H; j++) {
+        float2 m = bc(w.nbr_b[j]);
+        m = __ffma2_rn(bc(w.nbr_w[j][0]), d0, m); m = __ffma2_rn(bc(w.nbr_w[j][1]), d1, m);
+        m = __ffma2_rn(bc(w.nbr_w[j][2]), d2, m); m = __ffma2_rn(bc(w.nbr_w[j][3]), d3, m);
+        m = __ffma2_rn(bc(w.nbr_w[j][4]), d4, m); m = __ffma2_rn(bc(w.nbr_w[j][5]), d5, m);
+        m.x = fmaxf(m.x, 0.f); m.y = fmaxf(m.y, 0.f);
+        t2 = __ffma2_rn(bc(w.att_w[j]), m, t2);
+#pragma unroll
+        for (int a = 0; a < NZ; a++) hr[a] = __ffma2_rn(bc(w.head_w[a][H + j]), m, hr[a]);
+      }
+      float* o0 = s_row + (q - c0) * RS;
+      o0[0] = t2.x;
+#pragma unroll
+      for (int a = 0; a < NZ; a++) o0[1 + a] = hr[a].x;
+      if (q1 != q) {
+        float* o1 = s_row + (q1 - c0) * RS;
+        o1[0] = t2.y;
+#pragma unroll
+        for (int a = 0; a < NZ; a++) o1[1 + a] = hr[a].y;
+      }
     }
-    const float nm = fmaxf(mx, t);
-    const float sc = expf(mx - nm), p = expf(t - nm);   // first row: exp(-inf) = 0
-    s = fmaf(s, sc, p);
+    __syncthreads();
+    {  // phase 3: fold my agent's rows of this chunk
+      const int lo = my0 > c0 ? my0 : c0, hi = my1 < cend ? my1 : cend;
+      for (int q = lo; q < hi; q++) {
+        const float* o = s_row + (q - c0) * RS;
+        const float t = o[0];
+        const float nm = fmaxf(mx, t);
+        const float sc = expf(mx - nm), pw = expf(t - nm);   // first row: exp(-inf) = 0
+        s = fmaf(s, sc, pw);
 #pragma unroll
-    for (int a = 0; a < NZ; a++) acc[a] = fmaf(acc[a], sc, p * hr[a]);
-    mx = nm;
+        for (int a = 0; a < NZ; a++) acc[a] = fmaf(acc[a], sc, pw * o[1 + a]);
+        mx = nm;
+      }
+    }
+    __syncthreads();                    // before the next chunk overwrites s_row
   }
+  if (!valid) return;
   if (cnt > 0) {
     const float inv = 1.f / s;
 #pragma unroll
@@ -245,7 +294,7 @@ __global__ void __launch_bounds__(256) gae_kernel(const __grid_constant__ GaePar
 
 static int launch_actor(const PolicyParams& w, const PolicyIO& io, int n_actions, cudaStream_t st) {
   if (io.n_rows == 0) return 0;
-  const int block = 128;            // the kernel's counting sort assumes exactly 128
+  const int block = 128;            // = AG, the agents a block owns
   const int64_t grid = (io.n_rows + block - 1) / block;
   constexpr int V = GSM_POLICY_VALUE_HEADS;
   const unsigned gd = (unsigned)grid;
