@@ -655,13 +655,14 @@ def closed_loop_fused(cfg, n_envs, n_steps, local, rank, n_streams=1):
     env.close()
     return {"value": n_envs * cfg.n_agents * reps * T / (ms * 1e-3), "unit": UNIT, "steps": reps * T,
             "ms_per_step": ms / (reps * T),
-            "policy": "graph_actor_kernel<5> (this library, fp32, weights as kernel parameters) via gsm_collect; "
+            "policy": "graph_actor_kernel<5,0> (this library, fp32, weights as kernel parameters) via gsm_collect; "
                       f"CUDA graph of {2 * T} launches per {T}-step rollout per sub-shard ({max(1, n_streams)} "
                       "sub-shard(s), each its own actor -> env chain on its own stream) + reset per rollout",
             "actor_kernel_us": actor_us, "mean_valid_rows_per_agent": rows / n_agents,
             "actor_tflops": flops / (actor_us * 1e-6) / 1e12,
-            "actor_bound": "fp32 issue (FFMA with uniform-register weight operands); "
-                           "B200 fp32 peak 148 SM x 128 FMA/clk x 2 x 1.965 GHz = 74.5 TFLOP/s"}
+            "actor_bound": "fp32 issue / FMA pipe (packed FFMA2 with broadcast uniform-register weights); measured "
+                           "FFMA peak on this GPU 72 TFLOP/s (profiles/fma_peak.cu; nominal 148 SM x 128 FMA/clk x 2 x "
+                           "1.965 GHz = 74.5)"}
 
 
 def closed_loop(env, cfg, n_steps, dev):
