@@ -69,16 +69,23 @@ __device__ __forceinline__ void philox_p(uint32_t c0, uint32_t c1, uint32_t c2, 
 // NV = 0: actor only; NV = GSM_POLICY_VALUE_HEADS: the critics ride along as NV more rows of the head
 // (+2 FFMA per hidden unit and row), for collect loops that store value predictions.
 //
-// Work decomposition ("flattened rows").  A block owns 128 consecutive agents.  Phase 1: thread a
-// runs agent a's ego branch.  Phase 2: the block's valid neighbour rows — sum(cnt) of them, found
-// through an exclusive prefix of cnt — are one flat list of independent work items; thread t takes
-// items t, t+128, ... (agent by binary search in the prefix, 7 steps), computes that row's attention
-// score and head contribution and parks the 1 + NZ floats in shared memory.  Phase 3: thread a folds
-// its own agent's rows, in row order, into the online softmax.  Every lane of every warp carries a
-// real row in phase 2 whatever the per-agent counts are, and a 49 152-agent batch becomes ~250 000
-// threads' worth of items instead of 49 152 threads of very different length — the thread-per-agent
-// version had 20.8 (28.1 after a per-block counting sort by cnt) of 32 lanes active and 10 warps/SM.
-// Row items are processed in chunks of CH so that shared memory does not depend on K.
+// Work decomposition ("flattened rows").  A block owns 128 consecutive agents.  Phase 1: the ego
+// branch, agents (t, t + 64) packed into the two halves of float2 registers on warps 0-1.  Phase 2:
+// the block's valid neighbour rows — sum(cnt) of them, found through an exclusive prefix of cnt —
+// are one flat list of independent work items; a thread takes items q and q + 128 (agent by binary
+// search in the prefix, 7 steps), again packed in float2 halves, computes their attention scores and
+// head contributions and parks 1 + NZ floats per row in shared memory.  Phase 3: thread a folds its
+// own agent's rows, in row order, into the online softmax.  Every lane of every warp carries a real
+// row in phase 2 whatever the per-agent counts are (30 of 32 lanes active; the thread-per-agent
+// version had 20.8, and 28.1 after a per-block counting sort by cnt).  Row items are processed in
+// chunks of CH so that shared memory does not depend on K.
+//
+// Arithmetic: Blackwell's packed fp32 FMA (FFMA2, `fma.rn.f32x2`) with the weight as the BROADCAST
+// uniform scalar operand (`FFMA2 R, R.F32x2, UR.F32, R.F32x2`) — profiles/fma_peak.cu measures that
+// form at the full 127 FMA/clk/SM for half the issue slots of scalar FFMA, while a constant PAIR
+// operand (packing two hidden units instead of two rows) runs at 32.  Feature loads are scalar on
+// purpose: a 64-bit load pins (x, y) of one row to an aligned register pair and ptxas then
+// re-assembles every (row 0, row 1) operand pair with two MOVs per FFMA2.
 __device__ __forceinline__ float2 bc(float w) { return make_float2(w, w); }
 
 template <int NA, int NV>

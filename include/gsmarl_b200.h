@@ -6,7 +6,7 @@
  *   gsmarl/envs/mpe_env/env_wrappers.py          (GSMARL.egg-info/SOURCES.txt:11)
  *   gsmarl/envs/mpe_env/multiagent/environment.py (SOURCES.txt:15; classes named in readme.md:27-41)
  *   gsmarl/envs/mpe_env/multiagent/core.py        (SOURCES.txt:14)
- *   gsmarl/envs/mpe_env/multiagent/scenarios/*.py (SOURCES.txt:21-25)
+ *   gsmarl/envs/mpe_env/multiagent/scenarios/<name>.py (SOURCES.txt:21-25)
  * Those files are WITHHELD in the mounted reference (readme.md:1, "hidden during
  * review"); only the manifest lines above prove they are supposed to exist.  The
  * reference has no FFI of its own (pure Python, setup.py:12-25 builds no extension),
@@ -77,7 +77,7 @@ typedef enum gsm_entity_type {
 
 /*
  * World + scenario description.  Stands in for scenario.make_world(args)
- * (scenarios/*.py, SOURCES.txt:21-25) and the World constants of core.py
+ * (scenarios/<name>.py, SOURCES.txt:21-25) and the World constants of core.py
  * (SOURCES.txt:14).  Entities are indexed agents first (0..n_agents-1) then
  * landmarks (n_agents..n_agents+n_landmarks-1).  All pointer fields are HOST arrays
  * copied at gsm_create; none may be NULL unless stated.
@@ -165,7 +165,7 @@ int gsm_destroy(gsm_env* h);
 int gsm_get_io_sizes(const gsm_env* h, gsm_io_sizes* out);
 
 /* MultiAgentGraphConstrainEnv.reset (environment.py SOURCES.txt:15; scenario
- * reset_world, scenarios/*.py).  mask: NULL = every env; else device u8, env i is
+ * reset_world, scenarios/<name>.py).  mask: NULL = every env; else device u8, env i is
  * reset iff mask[i*mask_stride] != 0 (mask_stride = N lets a `done` buffer be
  * passed directly).  Writes obs / nbr_* / adj (and assign) of the reset envs only. */
 int gsm_reset(gsm_env* h, uint64_t seed, const uint8_t* mask, int64_t mask_stride,

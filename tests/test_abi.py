@@ -97,3 +97,35 @@ def test_product_never_imports_oracle():
                 s = open(os.path.join(d, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", s, flags=re.M), f
                 assert "gsm_oracle" not in s, f
+
+
+def test_ctypes_mirror_matches_the_header_as_compiled_by_gcc(tmp_path):
+    """sizeof / offsetof of every struct, taken from include/gsmarl_b200.h by a C compiler, against
+    the ctypes mirror in gs_marl_b200/abi.py (a silent mismatch would corrupt weights or pointers)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    checks = [("gsm_config", abi.GsmConfig, ["dtype", "dt", "spawn_extent", "discrete_u", "slot_table"]),
+              ("gsm_step_io", abi.GsmStepIO, ["actions", "nbr_feat", "assign"]),
+              ("gsm_io_sizes", abi.GsmIoSizes, ["agent_state", "adj_words", "real_bytes"]),
+              ("gsm_policy_weights", abi.GsmPolicyWeights, ["n_actions", "ego_w", "nbr_b", "att_b", "head_w",
+                                                            "head_b", "value_w", "value_b"]),
+              ("gsm_policy_io", abi.GsmPolicyIO, ["logits", "values", "n_rows", "seed", "max_nbrs", "greedy"])]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gsmarl_b200.h"', 'int main(void) {']
+    for cname, _, fields in checks:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ['  printf("abi %d\\n", GSM_ABI_VERSION);', '  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(got["abi"]) == abi.GSM_ABI_VERSION
+    for cname, ct, fields in checks:
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for f in fields:
+            assert int(got[f"{cname}.{f}"]) == getattr(ct, f).offset, (cname, f)
