@@ -110,3 +110,30 @@ def test_two_rank_gloo_sharded_rollout_equals_single():
     assert (state == env.agent_state).all()                 # sharding is invisible, bit-exact
     assert tot["env_steps"] == 5 * n_total and tot["agent_steps"] == 5 * n_total * 3
     assert tot["reward_sum"] == pytest.approx(rs, rel=1e-12) and tot["cost_sum"] == cs
+
+
+def test_make_env_argument_mapping_and_no_fallback():
+    """make_env.py mirror: all_args -> WorldConfig mapping is host logic; creating the env without a
+    device raises (never a CPU env)."""
+    import types
+
+    import torch
+
+    from gs_marl_b200 import abi, make_env
+    args = types.SimpleNamespace(scenario_name="polygon", num_agents=6, n_rollout_threads=10, episode_length=100, seed=3)
+    w = make_env.world_from_args(args)
+    assert w.n_agents == 6 and w.episode_length == 100 and w.dtype == "f32"
+    assert make_env.world_from_args(types.SimpleNamespace(scenario_name="navigation", num_agents=3,
+                                                          verification_mode=True)).dtype == "f64"
+    with pytest.raises(KeyError):
+        make_env.world_from_args(types.SimpleNamespace(scenario_name="simple_spread", num_agents=3))
+    with pytest.raises(ValueError):
+        make_env.world_from_args(types.SimpleNamespace(scenario_name="navigation", num_agents=0))
+    with pytest.raises(ValueError):
+        make_env.make_train_env(args, backend="jax")
+    with pytest.raises(ValueError):
+        make_env.make_train_env(types.SimpleNamespace(scenario_name="navigation", num_agents=3, n_rollout_threads=0))
+    if not torch.cuda.is_available():
+        for backend in ("numpy", "torch"):
+            with pytest.raises(abi.GsmError):
+                make_env.make_train_env(args, backend=backend)
