@@ -249,3 +249,29 @@ def test_gae_kernel_matches_oracle_on_a_collected_rollout():
     np.testing.assert_allclose(ret.cpu().numpy().reshape(T, -1, 2), r0, rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(adv.cpu().numpy().reshape(T, -1, 2), a0, rtol=1e-4, atol=1e-4)
     env.close()
+
+
+def test_oracle_reproduces_committed_policy_golden():
+    """tests/golden/policy_golden.npz (generator: tests/golden/make_policy_golden.py) pins the actor /
+    sampling / GAE oracle: the target the CUDA kernels are compared with must not drift."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policy_golden.npz"))
+    w = {k[2:]: g[k] for k in g.files if k.startswith("w_")}
+    a, lp, z, margin = P.act(w, g["obs"], g["feat"], g["cnt"], seed=99, step=7, row_offset=12345)
+    np.testing.assert_allclose(z, g["logits"], rtol=1e-10, atol=1e-10)
+    # float32 log may differ by an ulp between SIMD paths / numpy builds: tolerance, and actions only
+    # where the two largest perturbed logits are further apart than that could matter
+    np.testing.assert_allclose(P.gumbel(96, 5, 99, 7, 12345), g["gumbel"], rtol=1e-5, atol=1e-6)
+    safe = g["margin"] > 1e-4
+    assert safe.mean() > 0.95
+    np.testing.assert_array_equal(a[safe], g["actions"][safe])
+    lp, g_lp = lp[safe], g["logp"][safe]
+    np.testing.assert_allclose(lp, g_lp, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(P.values(w, g["obs"], g["feat"], g["cnt"]), g["values"], rtol=1e-12, atol=1e-12)
+    ret, adv = P.gae(g["gae_reward"], g["gae_cost"], g["gae_values"], g["gae_done"], 0.99, 0.95)
+    np.testing.assert_allclose(ret, g["gae_returns"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(adv, g["gae_adv"], rtol=1e-12, atol=1e-12)
+    # the weights in the fixture are the ones GraphAttentionActor(5, seed=2026) draws (init is part of the pin)
+    w2 = P.weights_from_state_dict(GraphAttentionActor(5, seed=2026).state_dict())
+    for k in w:
+        np.testing.assert_array_equal(w[k], w2[k])
