@@ -42,15 +42,16 @@ METRIC = "agent-steps/sec (graph obs+reward+cost) at 1/2/4/8 B200; % HBM rooflin
 UNIT = "agent-steps/s"
 
 
-def workload_config(n_gpus, extra=None):
-    c = {"workload": f"cooperative navigation, {N_AGENTS} agents, {ENVS_PER_GPU} envs per GPU, "
-                     "random discrete actions, fp32 production mode",
-         "n_agents": N_AGENTS, "envs_per_gpu": ENVS_PER_GPU, "global_envs": ENVS_PER_GPU * n_gpus,
-         "parallelism": f"env-sharded x{n_gpus}, no collective on the step path",
-         "spec_status": SPEC_STATUS}
-    if extra:
-        c.update(extra)
-    return c
+def workload_config(n_gpus, envs_per_gpu=ENVS_PER_GPU):
+    """The `config` object of BOTH arms (this repo's and `--impl reference`): identical keys and
+    values for the same command line, so that the driver can prove both ran the same workload.
+    How each arm runs it lives elsewhere (`method` here, `cpu_baseline.sample` there)."""
+    return {"workload": f"cooperative navigation, {N_AGENTS} agents, {envs_per_gpu} envs per GPU, "
+                        "random discrete actions, fp32 production mode",
+            "n_agents": N_AGENTS, "envs_per_gpu": envs_per_gpu, "global_envs": envs_per_gpu * n_gpus,
+            "episode_length": EPISODE_LEN,
+            "parallelism": f"env-sharded x{n_gpus}, no collective on the step path",
+            "spec_status": SPEC_STATUS}
 
 
 # ---------------------------------------------------------------------------------------
@@ -206,9 +207,9 @@ class CpuVecEnv:
             p.join(5)
 
 
-def cpu_rate(total_budget_s, n_steps):
-    """agent-steps/s of the reference-style port on all host cores, on a bounded sample sized
-    so that n_steps steps take about total_budget_s."""
+def cpu_sample_envs(total_budget_s, n_steps):
+    """Env count of the bounded CPU sample used by the GPU arm's `cpu_baseline` leg only (the
+    reference ARM never shrinks its workload): sized so n_steps steps take about total_budget_s."""
     cores = os.cpu_count() or 1
     probe = CpuVecEnv(cores * 2, cores)
     probe.step()
@@ -246,12 +247,18 @@ def cpu_c_oracle_rate(seconds=3.0):
 
 
 def run_reference(args):
+    """The CPU arm: the reference-STYLE numpy port in subprocess workers on all host cores, on EXACTLY
+    the GPU arm's workload — `--envs` (default 16384) envs per step, never a smaller sample: one
+    step is ~0.1 s on 16 cores, so the driver's --steps/--warmup finish in seconds.  Same `config`
+    as the GPU arm for the same command line."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warm = args.steps, args.warmup
-    cores, envs = cpu_rate(args.ref_budget, steps + warm)
+    cores, envs = os.cpu_count() or 1, args.envs
     vec = CpuVecEnv(envs, cores)
+    if vec.n_envs != envs:
+        raise SystemExit("reference arm could not build the full workload")
     for _ in range(warm):
         vec.step()
     t0 = time.perf_counter()
@@ -261,12 +268,13 @@ def run_reference(args):
     vec.close()
     value = envs * N_AGENTS * steps / dt
     sample = (f"reference-STYLE numpy port (oracle/py_env.py; GS-MARL's own env is withheld), fp64, "
-              f"{envs} envs per step in {cores} subprocess workers, {steps} steps")
+              f"the full workload: {envs} envs per step in {vec.cores} subprocess workers, {steps} steps")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, {"sample_envs_per_step": envs}),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(args.gpus, envs),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": vec.cores, "kind": "port", "sample": sample,
+                             "sample_envs_per_step": envs},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -320,105 +328,45 @@ def run_gpu(args):
     ring_bytes = sum(v.numel() * v.element_size() for v in ring.values())
 
     import ctypes as C
+    from bench_util import RolloutRegion, time_rollouts
     from gs_marl_b200.environment import StreamShardedEnv
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    io_full = env._make_io(ring, acts)                    # slot 0 of the [T][...] rollout buffers
-    env._check(env.lib.gsm_set_auto_reset(env._h, 1))
     # The timed region drives S contiguous sub-shards of this GPU's envs, each its own handle on
     # its own stream, all filling the SAME rollout buffer (gsm_set_slot_envs): the tail of one
     # shard's launch overlaps the body of the next (StreamShardedEnv docstring; --streams 1 = one handle).
     S = max(1, args.streams)
     sh_env = StreamShardedEnv(cfg, args.envs, n_streams=S, device=local, env_offset=rank * args.envs, seed=1)
     sh_env.reset()
-    sh_io = [sh._make_io({k: ring[k][0, lo:hi] for k in env.OUTPUTS}, acts[0, lo:hi])
-             for sh, (lo, hi) in zip(sh_env.shards, sh_env.bounds)]
-    sh_streams = [C.c_void_p(st.cuda_stream) for st in sh_env.streams]
-    lib = env.lib
 
-    def set_auto(flag):
-        for sh in sh_env.shards:
-            sh._check(lib.gsm_set_auto_reset(sh._h, int(flag)))
-
-    def run_steps(n):
-        """n env steps through the C ABI: fused rollouts of T steps (gsm_rollout), one launch per
-        sub-shard per T steps, round-robin over the shard streams, nothing joined in between; envs
-        finish an episode every EPISODE_LEN steps and are re-drawn inside the kernel."""
-        done = 0
-        while done < n:
-            m = min(T, n - done)
-            for sh, io, st in zip(sh_env.shards, sh_io, sh_streams):
-                sh._check(lib.gsm_rollout(sh._h, m, C.byref(io), st))
-            done += m
-
-    def timed(fn):
-        """CUDA events on the current stream around work enqueued on the shard streams: every
-        shard stream waits for the start event, the current stream waits for every shard stream."""
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for st in sh_env.streams:
-            st.wait_event(e0)
-        fn()
-        sh_env.join()
-        e1.record()
-        return e0, e1
-
-    set_auto(1)
+    # ---- THE timed region: K env steps = fused T-step launches on the S shard streams, captured in
+    # ONE CUDA graph (fork / join inside) and replayed `repeats` times back to back so that the
+    # region lasts >= --region-ms whatever K is; envs are re-drawn in-kernel every EPISODE_LEN
+    # steps (state and episode counters persist across replays); all nine outputs are written.
+    region = RolloutRegion(sh_env, acts, ring, K, T, auto_reset=True)
     sampler = ClockSampler(local); sampler.start()
-    run_steps(max(W, 3))
-    barrier()
-    l0 = sh_env.kernel_launches
+    warm_units = max(1, -(-max(W, 3) // (region.regions_per_unit * K)))
+    for _ in range(warm_units):
+        region.replay_unit()
+    torch.cuda.synchronize()
+    units = torch.tensor([region.calibrate(args.region_ms)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(units, op=dist.ReduceOp.MAX)           # every rank runs the same work
+    units = int(units.item())
     barrier()
     wall0 = time.time()
-    ev0, ev1 = timed(lambda: run_steps(K))
+    ms, repeats = region.run(units)
     barrier()
     wall1 = time.time()
-    ms = ev0.elapsed_time(ev1)
-    launches = sh_env.kernel_launches - l0
-    n_resets = K // EPISODE_LEN
-    if not any(wall0 <= ts <= wall1 for ts, _ in sampler.lines):
-        # the timed region was shorter than nvidia-smi's sampling period: keep the same kernel
-        # running (untimed) until a few samples exist, and say so in the record
-        wall0 = time.time()
-        while time.time() - wall0 < 0.6:
-            run_steps(T)
-            torch.cuda.synchronize()
-        wall1 = time.time()
-        clocks = sampler.stop(wall0, wall1)
-        clocks["window"] = "0.6 s of the same rollouts right after the timed region (region < sampling period)"
-    else:
-        clocks = sampler.stop(wall0, wall1)
+    clocks = sampler.stop(wall0, wall1)
+    launches = repeats * region.launches_per_region
+    bytes_region = region.bytes_per_region(cfg)
 
-    # dominant kernel, back to back, CUDA events: the variant of the timed region (compiled-in
-    # auto-reset, MODE 2) and the plain one (MODE 0); over the S shard streams (aggregate: all
-    # launches' bytes / elapsed) and as ONE launch over all envs on one stream
-    reps = max(2, min(40, K // T))
-
-    def time_rollouts(auto):
-        set_auto(auto)
-        sh_env.reset()
-        run_steps(T)
-        torch.cuda.synchronize()
-        k0, k1 = timed(lambda: run_steps(reps * T))
-        torch.cuda.synchronize()
-        return k0.elapsed_time(k1) / (reps * T)
-
-    def time_rollouts_one_stream(auto):
-        env.reset()
-        env.rollout(acts, out=ring, auto_reset=auto)
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for _ in range(reps):
-            env._check(env.lib.gsm_rollout(env._h, T, C.byref(io_full), stream))
-        k1.record()
-        torch.cuda.synchronize()
-        return k0.elapsed_time(k1) / (reps * T)
-    kern_ms = time_rollouts(True)
-    kern_plain_ms = time_rollouts(False)
-    one_ms = time_rollouts_one_stream(True)
-    one_plain_ms = time_rollouts_one_stream(False)
-    set_auto(1)
-    env._check(env.lib.gsm_set_auto_reset(env._h, 1))
+    # ---- the same kernel in other arrangements (explains the headline; same graph method, shorter) ----
+    side_ms = min(args.region_ms, 60.0)
+    plain = time_rollouts(sh_env, cfg, acts, ring, K, T, False, side_ms)       # MODE 0: no auto-reset
+    one_auto = time_rollouts(env, cfg, acts, ring, K, T, True, side_ms)        # ONE launch per T steps
+    one_plain = time_rollouts(env, cfg, acts, ring, K, T, False, side_ms)
+    env._check(env.lib.gsm_set_auto_reset(env._h, 0))
 
     # ---- un-fused API: one gsm_step launch per env step (what a policy-in-the-loop caller uses) ----
     io_slots = [env._make_io({k: v[sidx] for k, v in ring.items()}, acts[sidx]) for sidx in range(T)]
@@ -444,22 +392,19 @@ def run_gpu(args):
         Tl = 8
         bacts = torch.randint(0, 5, (Tl, nl, N_AGENTS), generator=gen, device=dev, dtype=torch.int32)
         bring = {k: big._alloc(k, (Tl,)) for k in big.OUTPUTS}
-        big.rollout(bacts, out=bring)
-        torch.cuda.synchronize()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        for _ in range(5):
-            big.rollout(bacts, out=bring)
-        b1.record()
-        torch.cuda.synchronize()
-        step_ms = b0.elapsed_time(b1) / (5 * Tl)
-        gbs = cfg.bytes_per_agent_step() * nl * N_AGENTS / (step_ms * 1e-3) / 1e9
+        r = time_rollouts(big, cfg, bacts, bring, Tl, Tl, True, side_ms)
         pk, _ = measured_peak()
-        large = {"envs": nl, "step_us": step_ms * 1e3, "achieved": gbs, "unit": "GB/s", "frac": gbs / pk,
-                 "agent_steps_per_s": nl * N_AGENTS / (step_ms * 1e-3),
+        large = {"envs": nl, "step_us": r["step_us"], "achieved": r["achieved"], "unit": "GB/s",
+                 "frac": r["achieved"] / pk, "agent_steps_per_s": nl * N_AGENTS / (r["step_us"] * 1e-6),
+                 "steps_per_launch": Tl,
                  "buffer_mb": sum(v.numel() * v.element_size() for v in bring.values()) / 1e6}
         big.close()
         del bring, bacts
+
+    # ---- BASELINE configs[2], [3], [4] in the same run, under the same clock record --------------
+    other = None
+    if args.configs:
+        other = other_configs(args, local, rank, world, dev)
 
     # ---- closed loop: a random-init graph policy (plain PyTorch, library kernels) picks the actions
     # from obs + neighbour rows every step; one gsm_step launch per env step (BASELINE configs[4]
@@ -502,39 +447,47 @@ def run_gpu(args):
     pcie_d2h_gbs = d2h * 20 / (time.perf_counter() - tp0) / 1e9
     del dsrc, hdst
 
-    tms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    cl_ms = [closed["ms"], closed["fused_actor"]["ms"]] if closed is not None else [0.0, 0.0]
+    tms = torch.tensor([ms, e2e_s * 1e3] + cl_ms, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     totals = stats.all_reduce(device=dev)        # the only collective: final stats gather
-    ms, e2e_ms = tms.tolist()
+    ms, e2e_ms, cl_torch_ms, cl_fused_ms = tms.tolist()
 
     if rank == 0:
-        agent_steps = args.envs * N_AGENTS * K * world
-        value = agent_steps / (ms * 1e-3)
+        agents = args.envs * N_AGENTS
+        value = agents * K * repeats * world / (ms * 1e-3)
+        step_us = ms * 1e3 / (repeats * K)
         peak, peak_src = measured_peak()
-        bytes_launch = cfg.bytes_per_agent_step() * args.envs * N_AGENTS
-        achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
-        # exact bytes of one fused T-step launch: state read+written once, not every step
-        state_rw = 2 * 4 * 4 * args.envs * N_AGENTS
-        bytes_fused = T * (bytes_launch - state_rw) + state_rw
-        achieved_fused = bytes_fused / (kern_ms * T * 1e-3) / 1e9
+        achieved = bytes_region * repeats / (ms * 1e-3) / 1e9
+        per_step_bytes = cfg.bytes_per_agent_step() * agents     # state r/w charged every step (r1 accounting)
+        region_desc = (f"{region.copies} K-step region(s) per CUDA graph" if K <= 2500 else
+                       "CUDA graphs of 2500-step chunks")
+
+        def variant(r):
+            return {"step_us": r["step_us"], "achieved": r["achieved"], "frac": r["achieved"] / peak}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "repeats": repeats, "ms_per_step": ms / (repeats * K), "timed_region_ms": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world, {
-                "envs_per_gpu": args.envs, "global_envs": args.envs * world,
+            "config": workload_config(world, args.envs),
+            "method": {
                 "l2_policy": f"outputs rotate through a {T}-slot rollout buffer of {ring_bytes / 1e6:.0f} MB "
                              "(> 126 MB L2); no explicit flush",
-                "episode": f"episode_length {EPISODE_LEN}: every env is re-drawn in-kernel {n_resets} times inside the "
-                           "timed region (gsm_set_auto_reset)",
-                "launch": f"{T} fused steps per kernel launch (gsm_rollout); {S} contiguous env sub-shards of "
-                          f"{args.envs // S} envs, one handle + one CUDA stream each, one launch per shard per "
-                          f"{T} steps, all writing the same rollout buffer (gsm_set_slot_envs)",
-                "streams": S}),
+                "episode": f"episode_length {EPISODE_LEN}: every env is re-drawn in-kernel every {EPISODE_LEN} steps "
+                           "(gsm_set_auto_reset; state persists across launches and graph replays)",
+                "launch": f"fused launches of min({T}, remaining) steps (gsm_rollout); {S} contiguous env sub-shards of "
+                          f"{args.envs // S} envs, one handle + one CUDA stream each, all writing the same rollout "
+                          f"buffer (gsm_set_slot_envs)",
+                "timed_region": f"the K = {K}-step region is captured in a CUDA graph ({region_desc}; shard streams fork "
+                                f"and join inside the graph) and replayed back to back: repeats = {repeats} regions in "
+                                f"{ms:.1f} ms between two CUDA events; ms_per_step = region time / (repeats * K); no "
+                                "host launch inside the events",
+                "streams": S},
             "env_steps_per_s": value / N_AGENTS,
             "clocks": clocks,
-            "e2e": {"value": args.envs * N_AGENTS * Ke * world / (e2e_ms * 1e-3), "unit": UNIT,
+            "e2e": {"value": agents * Ke * world / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "api": "GraphVecEnv.step -> gsm_step_host (pinned arena; 1 H2D + 1 kernel + 1 D2H)",
                     "host_affinity": numa,
@@ -547,30 +500,30 @@ def run_gpu(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(),
-                         "kernel": f"gsm::env_steps_kernel<float, NAVIGATION, 3, 6, P={spec_p}, MODE=2 (auto-reset)> "
-                                   f"(one launch = {T} fused steps; achieved is per step)",
-                         "how": f"aggregate over {S} concurrent shard streams: algorithmic bytes of all launches of "
-                                "the region / CUDA-event time between a fork event every shard stream waits on and "
-                                "a join of all shard streams (same kernel, same envs, same buffer as `value`)",
-                         "plain_variant_step_us": kern_plain_ms * 1e3,
-                         "one_stream": {"note": "the same envs as ONE launch per T steps on one stream (the state "
-                                                "before sub-shards; what a single ncu launch corresponds to)",
-                                        "step_us": one_ms * 1e3, "plain_variant_step_us": one_plain_ms * 1e3,
-                                        "achieved": bytes_launch / (one_ms * 1e-3) / 1e9,
-                                        "frac": bytes_launch / (one_ms * 1e-3) / 1e9 / peak},
-                         "launch_us": kern_ms * 1e3 * T, "step_us": kern_ms * 1e3,
-                         "algorithmic_bytes_per_launch": bytes_launch * T,
-                         "algorithmic_bytes_per_step": bytes_launch,
-                         "frac_fused_exact": achieved_fused / peak,
-                         "bytes_per_agent_step": cfg.bytes_per_agent_step(), "peak_source": peak_src,
+                         "kernel": f"gsm::env_steps_kernel<float, NAVIGATION, 3, 6, P={spec_p}, MODE=2 (auto-reset)>",
+                         "how": "THE timed region itself (same events as `value`): algorithmic bytes of every fused "
+                                "launch in it (WorldConfig.bytes_fused: action + all outputs per step; agent state, "
+                                "landmarks and step counter once per launch) / region time, max over ranks",
+                         "step_us": step_us,
+                         "algorithmic_bytes_per_region": bytes_region,
+                         "algorithmic_bytes_per_agent_step": bytes_region / (agents * K),
+                         "frac_per_step_accounting": per_step_bytes / (step_us * 1e-6) / 1e9 / peak,
+                         "per_step_accounting_note": f"round-1 figure: {cfg.bytes_per_agent_step()} B per agent-step, i.e. "
+                                                     "state read+write, landmarks and counter charged on EVERY step "
+                                                     "although a fused launch moves them once",
+                         "plain_variant": variant(plain),
+                         "one_stream": {"note": "the same envs as ONE launch per fused rollout on one stream (what a single "
+                                                "ncu launch corresponds to)",
+                                        "auto_reset": variant(one_auto), "plain": variant(one_plain)},
+                         "peak_source": peak_src,
                          "note": "layout is the declared one of SPEC.md §6 (reference layout unknown)"},
-            "single_step_api": {"value": args.envs * N_AGENTS * world / (single_us * 1e-6), "unit": UNIT,
+            "single_step_api": {"value": agents * world / (single_us * 1e-6), "unit": UNIT,
                                 "us_per_step": single_us, "steps": n_single,
-                                "note": "gsm_step, one kernel launch per env step, outputs to rotating slots"},
+                                "note": "gsm_step, one kernel launch per env step from Python, outputs to rotating slots"},
             "final_stats": totals,
         }
         if world == 1 and not args.no_cpu:
-            cores, envs = cpu_rate(args.cpu_budget, 10)
+            cores, envs = cpu_sample_envs(args.cpu_budget, 10)
             cvec = CpuVecEnv(envs, cores)
             cvec.step()
             t0 = time.perf_counter()
@@ -585,9 +538,13 @@ def run_gpu(args):
             line["cpu_baseline_c_port"] = cpu_c_oracle_rate()
         if world == 1 and args.large_envs > 0:
             line["roofline_large_batch"] = large
+        if other is not None:
+            line["configs"] = other
         if closed is not None:
-            closed["value"] *= world           # every rank runs the same closed loop on its shard
-            closed["fused_actor"]["value"] *= world
+            # every rank runs the same closed loop on its own shard: whole-job value from the MAX time
+            closed["value"] = agents * closed["steps"] * world / (cl_torch_ms * 1e-3)
+            f = closed["fused_actor"]
+            f["value"] = agents * f["steps"] * world / (cl_fused_ms * 1e-3)
             line["closed_loop"] = closed
 
         print(json.dumps(line), flush=True)
@@ -597,7 +554,78 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def closed_loop_fused(cfg, n_envs, n_steps, local, rank, n_streams=1):
+OTHER_CONFIGS = [   # BASELINE.json configs[2] and [3]: (label, scenario, N, envs per GPU, make_world kwargs)
+    ("configs[2] navigation 24 agents x 4096 envs", "navigation", 24, 4096, {"max_nbrs": 32}),
+    ("configs[2] navigation 48 agents x 4096 envs", "navigation", 48, 4096, {"max_nbrs": 32}),
+    ("configs[2] navigation 96 agents x 4096 envs", "navigation", 96, 4096, {"max_nbrs": 32}),
+    ("configs[3] polygon 6 agents x 16384 envs", "polygon", 6, 16384, {}),
+    ("configs[3] polygon 12 agents x 16384 envs", "polygon", 12, 16384, {}),
+    ("configs[3] line 6 agents x 16384 envs", "line", 6, 16384, {}),
+    ("configs[3] line 12 agents x 16384 envs", "line", 12, 16384, {}),
+]
+
+
+def other_configs(args, local, rank, world, dev):
+    """Device-resident step time of BASELINE.json configs[2] (navigation 24/48/96 agents x 4096 envs),
+    configs[3] (polygon / line, 6 and 12 agents, per-step batched assignment) and configs[4] (navigation
+    12 agents, 65536 envs over the job's GPUs, closed loop with a random-init graph actor), measured in
+    THIS run under the same clock record as the headline: fused rollouts with in-kernel auto-reset,
+    CUDA-graph replay for >= --config-ms, every rank runs its own copy (weak scaling, like the headline)
+    except configs[4], which shards a fixed 65536 envs (strong)."""
+    import torch
+    import torch.distributed as dist
+    from bench_util import time_rollouts
+    from gs_marl_b200 import scenarios
+    from gs_marl_b200.environment import MultiAgentGraphConstrainEnv, StreamShardedEnv
+    peak, _ = measured_peak()
+    rows, times = [], []
+    for label, scn, N, n_envs, kw in OTHER_CONFIGS:
+        cfg = scenarios.load(scn).make_world(N, dtype="f32", **kw)     # episode length: the scenario's own (25 / 100)
+        per_step = cfg.bytes_fused(n_envs, 1)
+        T = 25 if per_step * 25 < 6e9 else 8                 # rollout-buffer slots; always > L2
+        S = max(1, args.streams)
+        env = (StreamShardedEnv(cfg, n_envs, n_streams=S, device=local, env_offset=rank * n_envs, seed=5)
+               if S > 1 else MultiAgentGraphConstrainEnv(cfg, n_envs, device=local, env_offset=rank * n_envs, seed=5))
+        env.reset()
+        acts = torch.randint(0, 5, (T, n_envs, N), device=dev, dtype=torch.int32)
+        ring = {k: env._alloc(k, (T,)) for k in env.OUTPUTS}
+        r = time_rollouts(env, cfg, acts, ring, T, T, True, args.config_ms)
+        env.close()
+        rows.append({"config": label, "envs_per_gpu": n_envs, "n_agents": N, "steps_per_launch": T, "streams": S,
+                     "max_nbrs": cfg.max_nbrs, "episode_length": cfg.episode_length, "bytes_per_agent_step": cfg.bytes_fused(n_envs, T) / (n_envs * N * T),
+                     "buffer_mb": sum(v.numel() * v.element_size() for v in ring.values()) / 1e6,
+                     "regions": r["regions"], "region_ms": r["ms"], "_bytes": cfg.bytes_fused(n_envs, T)})
+        times.append(r["ms"])
+        del ring, acts
+        torch.cuda.empty_cache()
+    # configs[4]: closed loop, 65536 envs in total
+    n5 = 65536 // world
+    cfg5 = scenarios.load("navigation").make_world(12, dtype="f32", episode_length=EPISODE_LEN)
+    c5 = closed_loop_fused(cfg5, n5, max(EPISODE_LEN, args.config5_steps), local, rank, args.collect_streams,
+                           actor_alone=False)
+    times.append(c5["ms"])
+    t = torch.tensor(times, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = t.tolist()
+    for row, ms in zip(rows, t):
+        steps = row["regions"] * row["steps_per_launch"]
+        row["step_us"] = ms * 1e3 / steps
+        row["agent_steps_per_s"] = row["envs_per_gpu"] * row["n_agents"] * steps * world / (ms * 1e-3)
+        row["achieved"] = row.pop("_bytes") * row["regions"] / (ms * 1e-3) / 1e9
+        row["frac"] = row["achieved"] / peak
+        row["region_ms"] = ms
+    ms5 = t[-1]
+    rows.append({"config": f"configs[4] navigation 12 agents, 65536 envs over {world} GPU(s) ({n5} per GPU), closed loop: "
+                           "graph_actor_kernel + env step per step (gsm_collect, CUDA graph), reset per rollout",
+                 "envs_per_gpu": n5, "n_agents": 12, "scaling": "strong", "steps": c5["steps"],
+                 "step_us": ms5 * 1e3 / c5["steps"], "region_ms": ms5,
+                 "agent_steps_per_s": n5 * 12 * c5["steps"] * world / (ms5 * 1e-3),
+                 "bound": "actor kernel: fp32 issue (not HBM); env step: HBM write stream"})
+    return rows
+
+
+def closed_loop_fused(cfg, n_envs, n_steps, local, rank, n_streams=1, actor_alone=True):
     """Closed loop with THIS library's actor kernel and C-level collect loop (f1):
     gsm_collect = per env step one graph_actor_kernel launch (forward + Gumbel-max sampling +
     log-prob, weights in the kernel parameter space) and one env-step launch, written straight into
@@ -628,6 +656,9 @@ def closed_loop_fused(cfg, n_envs, n_steps, local, rank, n_streams=1):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    if not actor_alone:
+        env.close()
+        return {"ms": ms, "steps": reps * T}
     # the actor kernel alone on one slot of the buffer
     obs, graph = buf["obs"][1], buf.graph(1)
     out = (buf["actions"][0], buf["logp"][0])
@@ -654,7 +685,7 @@ def closed_loop_fused(cfg, n_envs, n_steps, local, rank, n_streams=1):
     flops = 2.0 * (n_agents * H * (6 + A) + rows * H * (6 + 1 + A))
     env.close()
     return {"value": n_envs * cfg.n_agents * reps * T / (ms * 1e-3), "unit": UNIT, "steps": reps * T,
-            "ms_per_step": ms / (reps * T),
+            "ms": ms, "ms_per_step": ms / (reps * T),
             "policy": "graph_actor_kernel<5,0> (this library, fp32, weights as kernel parameters) via gsm_collect; "
                       f"CUDA graph of {2 * T} launches per {T}-step rollout per sub-shard ({max(1, n_streams)} "
                       "sub-shard(s), each its own actor -> env chain on its own stream) + reset per rollout",
@@ -723,7 +754,7 @@ def closed_loop(env, cfg, n_steps, dev):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     return {"value": env.n_envs * cfg.n_agents * n_steps / (ms * 1e-3), "unit": UNIT, "steps": n_steps,
-            "ms_per_step": ms / n_steps,
+            "ms": ms, "ms_per_step": ms / n_steps,
             "policy": f"random-init graph-attention policy, hidden {H}, plain PyTorch (library kernels); {mode}"}
 
 
@@ -743,8 +774,13 @@ def main():
     ap.add_argument("--closed-loop-steps", type=int, default=1000)
     ap.add_argument("--collect-streams", type=int, default=1,
                     help="env sub-shards (streams) of the fused closed loop: one shard's actor overlaps another's env step")
+    ap.add_argument("--region-ms", type=float, default=300.0,
+                    help="minimum length of the timed region: the K-step region is replayed until it lasts this long")
+    ap.add_argument("--configs", type=int, default=1, help="1: add the BASELINE configs[2..4] block to the line")
+    ap.add_argument("--config-ms", type=float, default=60.0, help="timed length per entry of the configs block")
+    ap.add_argument("--config5-steps", type=int, default=100)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
-    ap.add_argument("--ref-budget", type=float, default=90.0)
+    ap.add_argument("--ref-budget", type=float, default=90.0, help="(ignored: the reference arm always runs the full workload)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

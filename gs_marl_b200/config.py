@@ -145,3 +145,16 @@ class WorldConfig:
                      + K * abi.GSM_NBR_FEAT_DIM * rb + 4 + 4 * self.adj_words + rb + rb + 1 + 4)
         per_env = L * 2 * rb + 2 * 4          # landmark positions read, step counter r/w
         return per_agent + (per_env + N - 1) // N
+
+    def bytes_fused(self, n_envs: int, n_steps: int) -> int:
+        """Algorithmic HBM bytes of ONE fused `n_steps`-step launch over `n_envs` envs
+        (gsm_rollout): the agent state, the landmark positions and the step counter cross HBM
+        once per LAUNCH (they live in registers / shared memory in between), the action and every
+        output once per STEP.  This is the roofline numerator of bench.py."""
+        rb = 4 if self.dtype == "f32" else 8
+        N, L, K = self.n_agents, self.n_landmarks, self.max_nbrs
+        act = 4 if self.action_mode == "discrete" else 2 * rb
+        stream = (act + abi.GSM_OBS_DIM * rb + K * 4 + K * abi.GSM_NBR_FEAT_DIM * rb + 4
+                  + 4 * self.adj_words + rb + rb + 1 + 4)           # per agent per step
+        once = N * 2 * 4 * rb + L * 2 * rb + 2 * 4                   # per env per launch
+        return n_envs * (n_steps * N * stream + once)

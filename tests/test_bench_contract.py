@@ -22,7 +22,7 @@ def _run(args, timeout):
 
 
 def test_reference_arm_line():
-    d = _run(["--impl", "reference", "--steps", "2", "--warmup", "1", "--ref-budget", "2"], 300)
+    d = _run(["--impl", "reference", "--steps", "2", "--warmup", "1", "--envs", "256"], 300)
     assert BASE_KEYS <= set(d) and d["impl"] == "reference"
     assert d["metric"] == json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
     assert d["unit"] == "agent-steps/s" and d["value"] > 0 and d["higher_is_better"] is True
@@ -30,14 +30,40 @@ def test_reference_arm_line():
     assert "withheld" in d["cpu_baseline"]["sample"]   # never presented as GS-MARL's own env
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["gpu_launches"] == 0 and "unpinned" in d["config"]["spec_status"]
+    # the reference arm never shrinks its workload: exactly the envs it was asked for, and the same
+    # `config` object the GPU arm prints for the same command line
+    assert d["config"]["envs_per_gpu"] == 256 and d["cpu_baseline"]["sample_envs_per_step"] == 256
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(1, 256)
 
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
-    d = _run(["--steps", "200", "--warmup", "25", "--e2e-steps", "10", "--closed-loop-steps", "25",
-              "--large-envs", "65536", "--cpu-budget", "2"], 600)
-    assert BASE_KEYS | {"clocks", "roofline"} <= set(d)
+    d = _run(["--steps", "20", "--warmup", "5", "--e2e-steps", "10", "--closed-loop-steps", "25",
+              "--large-envs", "65536", "--cpu-budget", "2", "--region-ms", "100", "--config-ms", "20",
+              "--config5-steps", "25"], 900)
+    assert BASE_KEYS | {"clocks", "roofline", "repeats", "configs", "method"} <= set(d)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(1)       # same object as the reference arm's
+    # the timed region: `repeats` K-step regions replayed from a CUDA graph, >= region-ms long, and
+    # value / ms_per_step / roofline all derived from that one region
+    assert d["steps"] == 20 and d["repeats"] >= 1 and d["timed_region_ms"] >= 100
+    assert abs(d["ms_per_step"] - d["timed_region_ms"] / (d["repeats"] * d["steps"])) < 1e-9
+    assert abs(d["value"] - 16384 * 3 / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
     r = d["roofline"]
+    assert abs(r["step_us"] - d["ms_per_step"] * 1e3) < 1e-6
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_agent_step"] * d["value"] / 1e9) / r["achieved"] < 1e-6
+    assert r["frac"] < r["frac_per_step_accounting"]      # state / landmarks / counter charged once per launch
+    assert d["clocks"]["window"] == "timed region" and d["clocks"]["samples"] >= 1
+    labels = [c["config"] for c in d["configs"]]
+    assert sum(l.startswith("configs[2]") for l in labels) == 3 and sum(l.startswith("configs[3]") for l in labels) == 4
+    assert sum(l.startswith("configs[4]") for l in labels) == 1
+    for c in d["configs"]:
+        assert c["step_us"] > 0 and c["agent_steps_per_s"] > 0
+        if not c["config"].startswith("configs[4]"):
+            assert 0.02 < c["frac"] < 1.2 and c["bytes_per_agent_step"] > 0
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert 0.05 < r["frac"] < 1.2 and r["traffic"] is None or r["traffic"] > 0
     assert d["gpu_launches"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 13221888
