@@ -157,9 +157,8 @@ def ncu_traffic():
 # CPU arm: reference-STYLE numpy port in subprocess workers (SubprocVecEnv lineage)
 def _cpu_worker(conn, n_envs, seed):
     import numpy as np
-    from gs_marl_b200 import scenarios
-    from oracle import gsm_oracle as O, py_env
-    cfg = scenarios.load("navigation").make_world(N_AGENTS, dtype="f64")
+    from oracle import gsm_oracle as O, py_env, worlds
+    cfg = worlds.make_world("navigation", N_AGENTS, dtype="f64")      # the oracle's own table of the workload
     init = O.OracleEnv(cfg, n_envs, env_offset=seed * 100003)
     init.reset(1)
     envs = [py_env.PyEnv(cfg) for _ in range(n_envs)]
@@ -227,11 +226,10 @@ def cpu_c_oracle_rate(seconds=3.0):
     """The C restatement of the same model on all cores (a much stronger CPU baseline than the
     reference's Python style) — reported for context."""
     import numpy as np
-    from gs_marl_b200 import scenarios
-    from oracle import gsm_oracle as O
+    from oracle import gsm_oracle as O, worlds
     cores = os.cpu_count() or 1
     O.set_threads(cores)
-    cfg = scenarios.load("navigation").make_world(N_AGENTS, dtype="f32")
+    cfg = worlds.make_world("navigation", N_AGENTS, dtype="f32")
     env = O.OracleEnv(cfg, ENVS_PER_GPU)
     env.reset(1)
     bufs = env.alloc_io()

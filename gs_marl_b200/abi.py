@@ -135,7 +135,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("GSM_LIB_PATH") or LIB_PATH      # GSM_LIB_PATH: A/B builds of the same ABI (profiles/)
     if not os.path.exists(p):
         raise GsmError(
             f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -631,8 +631,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
-  return __ddiv_rn(__dadd_rn(__dmul_rn((double)(hi >> 5), 67108864.0), (double)(lo >> 6)),
-                   9007199254740992.0);
+  // (hi53 * 2^26 + lo) / 2^53: the division by a power of two is an exact multiply by 2^-53
+  return __dmul_rn(__dadd_rn(__dmul_rn((double)(hi >> 5), 67108864.0), (double)(lo >> 6)),
+                   1.0 / 9007199254740992.0);
 }
 
 struct ResetParams {

@@ -19,7 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
-#include "../include/gsmarl_b200.h"
+#include "orc_types.h"
 
 /* Philox4x32-10 (Salmon et al., SC'11), counter (c0..c3), key (k0,k1). SPEC §8. */
 static void orc_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,

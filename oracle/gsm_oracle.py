@@ -10,8 +10,7 @@ import subprocess
 
 import numpy as np
 
-from gs_marl_b200 import abi
-from gs_marl_b200.config import WorldConfig
+from . import worlds
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_DIR, "libgsm_oracle.so")
@@ -19,8 +18,7 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_DIR, f) for f in ("gsm_oracle.c", "gsm_oracle_impl.h", "Makefile")]
-    srcs.append(os.path.join(_DIR, "..", "include", "gsmarl_b200.h"))
+    srcs = [os.path.join(_DIR, f) for f in ("gsm_oracle.c", "gsm_oracle_impl.h", "orc_types.h", "Makefile")]
     if force or not os.path.exists(_SO) or any(
             os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs if os.path.exists(s)):
         subprocess.run(["make", "-C", _DIR, "-s", "-B"], check=True, capture_output=True)
@@ -33,7 +31,7 @@ def lib() -> C.CDLL:
         if not os.path.exists(_SO):
             build()
         _lib = C.CDLL(_SO)
-        cfgp, iop = C.POINTER(abi.GsmConfig), C.POINTER(abi.GsmStepIO)
+        cfgp, iop = C.POINTER(worlds.OrcConfig), C.POINTER(worlds.OrcStepIO)
         for sfx in ("f64", "f32"):
             getattr(_lib, f"orc_step_{sfx}").argtypes = [cfgp, C.c_int64, C.c_void_p, C.c_void_p,
                                                          C.c_void_p, iop]
@@ -78,7 +76,10 @@ def lsa(cost: np.ndarray) -> np.ndarray:
 class OracleEnv:
     """Batched oracle env holding numpy state; same buffers as gsm_step_io."""
 
-    def __init__(self, cfg: WorldConfig, n_envs: int, env_offset: int = 0):
+    def __init__(self, cfg, n_envs: int, env_offset: int = 0):
+        # `cfg`: an oracle World, or any object carrying the INPUT fields (worlds.as_world re-derives
+        # shapes and slot tables from SPEC.md itself and rejects a caller's table that disagrees)
+        cfg = worlds.as_world(cfg)
         self.cfg, self.n_envs, self.env_offset = cfg, n_envs, env_offset
         self._c, self._keep = cfg.to_c()
         self._sfx = cfg.dtype
@@ -92,9 +93,9 @@ class OracleEnv:
         return {k: np.zeros(s, d) for k, (d, s) in self.cfg.io_shapes(self.n_envs).items()}
 
     @staticmethod
-    def _io_struct(bufs: dict) -> abi.GsmStepIO:
-        io = abi.GsmStepIO()
-        for k in abi.GsmStepIO.FIELDS:
+    def _io_struct(bufs: dict) -> worlds.OrcStepIO:
+        io = worlds.OrcStepIO()
+        for k in worlds.OrcStepIO.FIELDS:
             a = bufs.get(k)
             setattr(io, k, None if a is None else a.ctypes.data)
         return io

@@ -26,11 +26,11 @@ static REAL ORC(softplus)(REAL x) {
  * Returns 0, or -1 if infeasible (cannot happen for finite costs).
  */
 int ORC(lsa)(const REAL* cost, int n, int32_t* col4row_out) {
-  REAL u[GSM_MAX_LSA_N], v[GSM_MAX_LSA_N], spc[GSM_MAX_LSA_N];
-  int path[GSM_MAX_LSA_N], col4row[GSM_MAX_LSA_N], row4col[GSM_MAX_LSA_N];
-  int remaining[GSM_MAX_LSA_N];
-  unsigned char SR[GSM_MAX_LSA_N], SC[GSM_MAX_LSA_N];
-  if (n < 1 || n > GSM_MAX_LSA_N) return -1;
+  REAL u[ORC_MAX_LSA_N], v[ORC_MAX_LSA_N], spc[ORC_MAX_LSA_N];
+  int path[ORC_MAX_LSA_N], col4row[ORC_MAX_LSA_N], row4col[ORC_MAX_LSA_N];
+  int remaining[ORC_MAX_LSA_N];
+  unsigned char SR[ORC_MAX_LSA_N], SC[ORC_MAX_LSA_N];
+  if (n < 1 || n > ORC_MAX_LSA_N) return -1;
   for (int a = 0; a < n; a++) { u[a] = 0; v[a] = 0; path[a] = -1; col4row[a] = -1; row4col[a] = -1; }
   for (int cur = 0; cur < n; cur++) {
     REAL minval = 0;
@@ -69,17 +69,17 @@ int ORC(lsa)(const REAL* cost, int n, int32_t* col4row_out) {
 }
 
 /* SPEC §5: slots + cost matrix + solve for one env; targets[i] = slot of agent i. */
-static void ORC(targets)(const gsm_config* c, const REAL* ag, const REAL* lm, int32_t* assign,
+static void ORC(targets)(const orc_config* c, const REAL* ag, const REAL* lm, int32_t* assign,
                          REAL* tx, REAL* ty) {
   const int N = c->n_agents;
-  if (c->scenario == GSM_SCN_NAVIGATION) {
+  if (c->scenario == ORC_SCN_NAVIGATION) {
     for (int i = 0; i < N; i++) { assign[i] = i; tx[i] = lm[2 * i]; ty[i] = lm[2 * i + 1]; }
     return;
   }
-  REAL sx[GSM_MAX_LSA_N], sy[GSM_MAX_LSA_N];
-  REAL cost[GSM_MAX_LSA_N * GSM_MAX_LSA_N];
+  REAL sx[ORC_MAX_LSA_N], sy[ORC_MAX_LSA_N];
+  REAL cost[ORC_MAX_LSA_N * ORC_MAX_LSA_N];
   for (int k = 0; k < N; k++) {
-    if (c->scenario == GSM_SCN_POLYGON) {
+    if (c->scenario == ORC_SCN_POLYGON) {
       REAL R = (REAL)c->polygon_radius;
       sx[k] = lm[0] + R * (REAL)c->slot_table[2 * k];
       sy[k] = lm[1] + R * (REAL)c->slot_table[2 * k + 1];
@@ -101,8 +101,8 @@ static void ORC(targets)(const gsm_config* c, const REAL* ag, const REAL* lm, in
 }
 
 /* SPEC §5-7 on the current state of one env.  with_rcd: also reward/cost/done. */
-static void ORC(observe_env)(const gsm_config* c, const REAL* ag, const REAL* lm, int32_t t,
-                             int64_t env, const gsm_step_io* io, int with_rcd) {
+static void ORC(observe_env)(const orc_config* c, const REAL* ag, const REAL* lm, int32_t t,
+                             int64_t env, const orc_step_io* io, int with_rcd) {
   const int N = c->n_agents, L = c->n_landmarks, E = N + L, K = c->max_nbrs;
   const int W = (E + 31) / 32;
   REAL* tx = (REAL*)malloc(sizeof(REAL) * 2 * (size_t)N);
@@ -115,7 +115,7 @@ static void ORC(observe_env)(const gsm_config* c, const REAL* ag, const REAL* lm
     const REAL px = ag[4 * i], py = ag[4 * i + 1], vx = ag[4 * i + 2], vy = ag[4 * i + 3];
     const int64_t row = env * N + i;
     if (io->obs) {
-      REAL* o = (REAL*)io->obs + row * GSM_OBS_DIM;
+      REAL* o = (REAL*)io->obs + row * ORC_OBS_DIM;
       o[0] = vx; o[1] = vy; o[2] = px; o[3] = py; o[4] = tx[i] - px; o[5] = ty[i] - py;
     }
     if (io->assign) io->assign[row] = asg[i];
@@ -130,13 +130,13 @@ static void ORC(observe_env)(const gsm_config* c, const REAL* ag, const REAL* lm
       const REAL dx = ex - px, dy = ey - py;
       const REAL dist = R_SQRT(dx * dx + dy * dy);
       int nb = dist < Rs;
-      if (c->own_goal_always && c->scenario == GSM_SCN_NAVIGATION && e == N + i) nb = 1;
+      if (c->own_goal_always && c->scenario == ORC_SCN_NAVIGATION && e == N + i) nb = 1;
       if (nb) {
         words[e >> 5] |= 1u << (e & 31);
         if (cnt < K) {
           if (io->nbr_idx) io->nbr_idx[row * K + cnt] = e;
           if (io->nbr_feat) {
-            REAL* f = (REAL*)io->nbr_feat + (row * K + cnt) * GSM_NBR_FEAT_DIM;
+            REAL* f = (REAL*)io->nbr_feat + (row * K + cnt) * ORC_NBR_FEAT_DIM;
             f[0] = dx; f[1] = dy; f[2] = evx - vx; f[3] = evy - vy; f[4] = dist; f[5] = (REAL)c->type[e];
           }
           cnt++;
@@ -145,14 +145,14 @@ static void ORC(observe_env)(const gsm_config* c, const REAL* ag, const REAL* lm
       const REAL dmin = (REAL)c->size[i] + (REAL)c->size[e];
       if (dist < dmin) {
         if (e < N) ncol++;
-        else if (c->cost_obstacles && c->type[e] == GSM_ENT_OBSTACLE) ncol++;
+        else if (c->cost_obstacles && c->type[e] == ORC_ENT_OBSTACLE) ncol++;
       }
     }
     for (int k = cnt; k < K; k++) {
       if (io->nbr_idx) io->nbr_idx[row * K + k] = -1;
       if (io->nbr_feat) {
-        REAL* f = (REAL*)io->nbr_feat + (row * K + k) * GSM_NBR_FEAT_DIM;
-        for (int q = 0; q < GSM_NBR_FEAT_DIM; q++) f[q] = 0;
+        REAL* f = (REAL*)io->nbr_feat + (row * K + k) * ORC_NBR_FEAT_DIM;
+        for (int q = 0; q < ORC_NBR_FEAT_DIM; q++) f[q] = 0;
       }
     }
     if (io->nbr_cnt) io->nbr_cnt[row] = cnt;
@@ -182,7 +182,7 @@ static void ORC(observe_env)(const gsm_config* c, const REAL* ag, const REAL* lm
 }
 
 /* SPEC §2-4 for one env, in place. */
-static void ORC(physics_env)(const gsm_config* c, REAL* ag, const REAL* lm, const void* actions,
+static void ORC(physics_env)(const orc_config* c, REAL* ag, const REAL* lm, const void* actions,
                              int64_t env) {
   const int N = c->n_agents, L = c->n_landmarks, E = N + L;
   REAL* nv = (REAL*)malloc(sizeof(REAL) * 4 * (size_t)N);
@@ -190,7 +190,7 @@ static void ORC(physics_env)(const gsm_config* c, REAL* ag, const REAL* lm, cons
   const REAL dt = (REAL)c->dt, damp = (REAL)c->damping;
   for (int i = 0; i < N; i++) {
     REAL ux = 0, uy = 0;
-    if (c->action_mode == GSM_ACT_DISCRETE) {
+    if (c->action_mode == ORC_ACT_DISCRETE) {
       int a = ((const int32_t*)actions)[env * N + i];
       if (a >= 0 && a < c->n_discrete_actions) { ux = (REAL)c->discrete_u[2 * a]; uy = (REAL)c->discrete_u[2 * a + 1]; }
     } else {
@@ -229,7 +229,7 @@ static void ORC(physics_env)(const gsm_config* c, REAL* ag, const REAL* lm, cons
 }
 
 typedef struct ORC(job) {
-  const gsm_config* c; REAL* ag; const REAL* lm; int32_t* t; const gsm_step_io* io; int physics;
+  const orc_config* c; REAL* ag; const REAL* lm; int32_t* t; const orc_step_io* io; int physics;
 } ORC(job);
 
 static void ORC(range)(int64_t lo, int64_t hi, void* ctx) {
@@ -246,22 +246,22 @@ static void ORC(range)(int64_t lo, int64_t hi, void* ctx) {
   }
 }
 
-int ORC(step)(const gsm_config* c, int64_t n_envs, REAL* agent_state, const REAL* lm_pos,
-              int32_t* step_count, const gsm_step_io* io) {
+int ORC(step)(const orc_config* c, int64_t n_envs, REAL* agent_state, const REAL* lm_pos,
+              int32_t* step_count, const orc_step_io* io) {
   ORC(job) jb = {c, agent_state, lm_pos, step_count, io, 1};
   orc_parallel_for(n_envs, ORC(range), &jb);
   return 0;
 }
 
-int ORC(observe)(const gsm_config* c, int64_t n_envs, const REAL* agent_state, const REAL* lm_pos,
-                 const int32_t* step_count, const gsm_step_io* io) {
+int ORC(observe)(const orc_config* c, int64_t n_envs, const REAL* agent_state, const REAL* lm_pos,
+                 const int32_t* step_count, const orc_step_io* io) {
   ORC(job) jb = {c, (REAL*)agent_state, lm_pos, (int32_t*)step_count, io, 0};
   orc_parallel_for(n_envs, ORC(range), &jb);
   return 0;
 }
 
 /* SPEC §8. */
-int ORC(reset)(const gsm_config* c, int64_t n_envs, int64_t env_offset, uint64_t seed,
+int ORC(reset)(const orc_config* c, int64_t n_envs, int64_t env_offset, uint64_t seed,
                const uint8_t* mask, int64_t mask_stride, REAL* agent_state, REAL* lm_pos,
                int32_t* step_count, int32_t* episode) {
   const int N = c->n_agents, L = c->n_landmarks, E = N + L;

@@ -13,8 +13,7 @@ from __future__ import annotations
 import numpy as np
 from scipy.optimize import linear_sum_assignment
 
-from gs_marl_b200 import abi
-from gs_marl_b200.config import WorldConfig
+from . import worlds
 
 
 class Entity:
@@ -27,7 +26,7 @@ class Entity:
 class World:
     """SPEC §2-4."""
 
-    def __init__(self, cfg: WorldConfig):
+    def __init__(self, cfg):
         self.cfg = cfg
         R = cfg.np_real
         self.R = R
@@ -75,7 +74,8 @@ class World:
 class PyEnv:
     """One env; step(actions) -> dict of per-agent arrays (same names as gsm_step_io)."""
 
-    def __init__(self, cfg: WorldConfig):
+    def __init__(self, cfg):
+        cfg = worlds.as_world(cfg)        # shapes / slot tables re-derived from SPEC.md, not taken from the caller
         self.cfg, self.world = cfg, World(cfg)
 
     def set_state(self, agent_state, landmark_pos, t=0):
@@ -144,7 +144,7 @@ class PyEnv:
                                                    b.p_vel[1] - a.p_vel[1], dist, R(b.type)]
                         cnt += 1
                 if dist < a.size + b.size:
-                    if b.idx < N or (c.cost_obstacles and b.type == abi.GSM_ENT_OBSTACLE):
+                    if b.idx < N or (c.cost_obstacles and b.type == worlds.ENT_OBSTACLE):
                         ncol += 1
             out["nbr_cnt"][i] = cnt
             gx, gy = tg[0] - a.p_pos[0], tg[1] - a.p_pos[1]

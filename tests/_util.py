@@ -5,6 +5,7 @@ import os
 import numpy as np
 
 from gs_marl_b200 import scenarios
+from oracle import worlds as oracle_worlds
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 INT_KEYS = ("nbr_idx", "nbr_cnt", "adj", "done", "assign")
@@ -23,7 +24,36 @@ def golden_path(name, N, kw):
 
 
 def make_cfg(name, N, dtype, **kw):
-    return scenarios.load(name).make_world(N, dtype=dtype, **kw)
+    """The PRODUCT's world for (name, N, kwargs) — after checking, field by field, that it equals
+    the ORACLE's own literal table for the same request (oracle/worlds.py shares no code with
+    gs_marl_b200/scenarios + presets): a wrong constant, slot table or shape on either side fails
+    here instead of being handed to both implementations as a common input."""
+    cfg = scenarios.load(name).make_world(N, dtype=dtype, **kw)
+    assert_same_world(cfg, oracle_worlds.make_world(name, N, dtype=dtype, **kw), f"{name}-{N} {kw}")
+    return cfg
+
+
+def oracle_world(name, N, dtype, **kw):
+    return oracle_worlds.make_world(name, N, dtype=dtype, **kw)
+
+
+def assert_same_world(product_cfg, oracle_world_, ctx=""):
+    for f in oracle_worlds.INPUT_FIELDS + ("slot_table",):
+        a, b = getattr(product_cfg, f), getattr(oracle_world_, f)
+        if isinstance(a, (str, bool, int)) and not isinstance(a, float):
+            assert a == b, f"{ctx}: {f}: product {a!r} != oracle table {b!r}"
+        elif a is None or b is None:
+            assert a is None and b is None, f"{ctx}: {f}: product {a!r} != oracle table {b!r}"
+        else:
+            assert np.array_equal(np.asarray(a, np.float64), np.asarray(b, np.float64)), \
+                f"{ctx}: {f}: product {a!r} != oracle table {b!r}"
+    n = 7
+    ps, os_ = product_cfg.io_shapes(n), oracle_world_.io_shapes(n)
+    assert set(ps) == set(os_), ctx
+    for k in ps:
+        assert np.dtype(ps[k][0]) == np.dtype(os_[k][0]) and tuple(ps[k][1]) == tuple(os_[k][1]), \
+            f"{ctx}: io_shapes[{k}]: product {ps[k]} != oracle {os_[k]}"
+    assert product_cfg.adj_words == oracle_world_.adj_words, ctx
 
 
 def random_actions(cfg, rng, lead):

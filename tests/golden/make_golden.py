@@ -21,8 +21,7 @@ from scipy.optimize import linear_sum_assignment
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from gs_marl_b200 import scenarios  # noqa: E402
-from oracle import gsm_oracle as O, py_env  # noqa: E402
+from oracle import gsm_oracle as O, py_env, worlds  # noqa: E402   (oracle/ only: no product import)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -67,9 +66,9 @@ TRAJ = [("navigation", 3, {}), ("navigation", 6, {"share_reward": True}),
         ("navigation", 4, {"action_mode": "continuous", "max_nbrs": 3, "own_goal_always": False})]
 
 
-def make_traj():
+def make_traj(out_dir=HERE):
     for name, N, kw in TRAJ:
-        cfg = scenarios.load(name).make_world(N, dtype="f64", **kw)
+        cfg = worlds.make_world(name, N, dtype="f64", **kw)      # the oracle's own literal tables
         B, T = 4, 25
         rng = np.random.default_rng(zlib.crc32(f"{name}{N}".encode()))
         env = O.OracleEnv(cfg, B)
@@ -94,11 +93,14 @@ def make_traj():
                 else:
                     rec[k].append(np.stack([o[k] for o in outs]))
         tag = f"traj_{name}_{N}" + ("_" + "_".join(f"{a}-{b}" for a, b in sorted(kw.items())) if kw else "")
-        np.savez_compressed(os.path.join(HERE, tag + ".npz"), agent_state0=ag0, landmark_pos=lm0,
+        np.savez_compressed(os.path.join(out_dir, tag + ".npz"), agent_state0=ag0, landmark_pos=lm0,
                             actions=acts, **{k: np.stack(v) for k, v in rec.items()})
         print(tag, "cost events:", int(np.stack(rec["cost"]).sum()))
 
 
 if __name__ == "__main__":
-    make_lsa()
-    make_traj()
+    if len(sys.argv) > 2 and sys.argv[1] == "--traj-only":     # tests: regenerate into a scratch directory
+        make_traj(sys.argv[2])
+    else:
+        make_lsa()
+        make_traj()

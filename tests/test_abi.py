@@ -129,3 +129,52 @@ def test_ctypes_mirror_matches_the_header_as_compiled_by_gcc(tmp_path):
         assert int(got[cname]) == C.sizeof(ct), cname
         for f in fields:
             assert int(got[f"{cname}.{f}"]) == getattr(ct, f).offset, (cname, f)
+
+
+def test_oracle_types_agree_with_the_public_header(tmp_path):
+    """oracle/orc_types.h is declared independently of include/gsmarl_b200.h (the oracle must not
+    inherit a mistake of the product's header); a C compiler checks that every field of both config
+    and io structs sits at the same offset, and that the oracle's ctypes mirror matches its header."""
+    import shutil
+    import subprocess
+    from oracle import worlds
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    cfg_fields = [n for n, _ in worlds.OrcConfig._fields_]
+    io_fields = list(worlds.OrcStepIO.FIELDS)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gsmarl_b200.h"', '#include "orc_types.h"',
+             'int main(void) {', '  printf("sizeof_cfg %zu %zu\\n", sizeof(gsm_config), sizeof(orc_config));',
+             '  printf("sizeof_io %zu %zu\\n", sizeof(gsm_step_io), sizeof(orc_step_io));']
+    for f in cfg_fields:
+        lines.append(f'  printf("cfg.{f} %zu %zu\\n", offsetof(gsm_config, {f}), offsetof(orc_config, {f}));')
+    for f in io_fields:
+        lines.append(f'  printf("io.{f} %zu %zu\\n", offsetof(gsm_step_io, {f}), offsetof(orc_step_io, {f}));')
+    lines += ['  printf("dims %d %d\\n", GSM_OBS_DIM == ORC_OBS_DIM && GSM_NBR_FEAT_DIM == ORC_NBR_FEAT_DIM && '
+              'GSM_MAX_LSA_N == ORC_MAX_LSA_N, (int)GSM_ENT_OBSTACLE == (int)ORC_ENT_OBSTACLE && '
+              '(int)GSM_SCN_LINE == (int)ORC_SCN_LINE && (int)GSM_ACT_CONTINUOUS == (int)ORC_ACT_CONTINUOUS);',
+              '  return 0;', '}']
+    src = tmp_path / "layout2.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout2"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I",
+                    os.path.join(ROOT, "oracle"), str(src), "-o", str(exe)], check=True)
+    rows = [ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()]
+    for name, a, b in rows:
+        if name == "dims":
+            assert a == "1" and b == "1"
+            continue
+        assert a == b, name
+        if name.startswith("cfg."):
+            assert int(b) == getattr(worlds.OrcConfig, name[4:]).offset, name
+        elif name.startswith("io."):
+            assert int(b) == getattr(worlds.OrcStepIO, name[3:]).offset, name
+    assert dict((r[0], r[2]) for r in rows)["sizeof_cfg"] == str(C.sizeof(worlds.OrcConfig))
+    assert (worlds.OBS_DIM, worlds.NBR_FEAT_DIM) == (abi.GSM_OBS_DIM, abi.GSM_NBR_FEAT_DIM)
+
+
+def test_oracle_never_imports_product():
+    for f in os.listdir(os.path.join(ROOT, "oracle")):
+        if f.endswith((".py", ".c", ".h")):
+            s = open(os.path.join(ROOT, "oracle", f)).read()
+            assert not re.search(r"^\s*(from|import)\s+gs_marl_b200\b", s, flags=re.M), f
+            assert "include/gsmarl_b200.h" not in s.replace("independent of include/gsmarl_b200.h", ""), f

@@ -151,3 +151,44 @@ def test_contact_forces_are_equal_and_opposite_and_match_softplus():
     assert out["cost"].tolist() == [[1.0, 1.0]] or out["cost"].tolist() == [[0.0, 0.0]]
     new_d = np.hypot(*(e.agent_state[0, 1, :2] - e.agent_state[0, 0, :2]))
     assert (new_d < 0.2) == bool(out["cost"][0, 0])                  # cost is taken on the post-step state
+
+
+def test_oracle_reproduces_goldens_without_the_product_package(tmp_path):
+    """the oracle builds its worlds from its OWN literal tables (oracle/worlds.py).
+    With `gs_marl_b200` made un-importable, tests/golden/make_golden.py regenerates every committed
+    trajectory bit for bit."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    blocker = (
+        "import sys, importlib.abc\n"
+        "class B(importlib.abc.MetaPathFinder):\n"
+        "    def find_spec(self, name, path=None, target=None):\n"
+        "        if name == 'gs_marl_b200' or name.startswith('gs_marl_b200.'):\n"
+        "            raise ImportError('product package blocked for this test')\n"
+        "sys.meta_path.insert(0, B())\n"
+        f"sys.argv = ['make_golden.py', '--traj-only', {str(tmp_path)!r}]\n"
+        "import runpy\n"
+        f"runpy.run_path({os.path.join(root, 'tests', 'golden', 'make_golden.py')!r}, run_name='__main__')\n"
+        "assert not any(m.startswith('gs_marl_b200') for m in sys.modules)\n")
+    subprocess.run([sys.executable, "-c", blocker], check=True, cwd=root, timeout=600)
+    for name, N, kw in GOLDEN_TRAJ:
+        want, got = np.load(golden_path(name, N, kw)), np.load(os.path.join(tmp_path, os.path.basename(golden_path(name, N, kw))))
+        assert set(want.files) == set(got.files)
+        for k in want.files:
+            assert np.array_equal(want[k], got[k]), (name, N, k)
+
+
+def test_oracle_tables_match_product_scenarios():
+    """The two independently written world tables (oracle/worlds.py, gs_marl_b200/scenarios + presets)
+    agree for every BASELINE.json configuration and every golden trajectory."""
+    from tests._util import assert_same_world, oracle_world
+    from gs_marl_b200 import scenarios
+    cases = list(GOLDEN_TRAJ) + [("navigation", n, {}) for n in (3, 6, 12)] + \
+        [("navigation", n, {"max_nbrs": 32}) for n in (24, 48, 96)] + \
+        [(s, n, {}) for s in ("polygon", "line", "simple_formation", "simple_line") for n in (3, 6, 12)]
+    for name, N, kw in cases:
+        for dt in ("f32", "f64"):
+            assert_same_world(scenarios.load(name).make_world(N, dtype=dt, **kw), oracle_world(name, N, dt, **kw),
+                              f"{name}-{N}")
