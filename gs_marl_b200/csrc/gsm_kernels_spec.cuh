@@ -16,26 +16,6 @@
 #pragma once
 #include "gsm_kernels.cuh"
 
-// A/B switches of the specialised kernel (profiles/sweep_nav3.py builds variants with -D...):
-//   GSM_SPEC_SEG   1: auto-reset (MODE 2) runs the plain step loop in segments that end where the
-//                     first env of the warp finishes its episode; the re-draw sits between segments
-//                     and keeps nothing live across the hot loop (episode counter and landmarks go
-//                     straight to global memory)
-//   GSM_SPEC_CARRY 1: the pair geometry (dx, dy, dist) of step s's graph pass is the geometry of step
-//                     s+1's force pass (same positions): carried in registers instead of recomputed
-#ifndef GSM_SPEC_SEG
-#define GSM_SPEC_SEG 1
-#endif
-#ifndef GSM_SPEC_CARRY
-#define GSM_SPEC_CARRY 0
-#endif
-#ifndef GSM_SPEC_ROLES_M2      // 1: the auto-reset variant uses 4 lane roles for the per-agent scalars at P = 4
-#define GSM_SPEC_ROLES_M2 1
-#endif
-#if GSM_SPEC_CARRY && !GSM_SPEC_SEG
-#error "GSM_SPEC_CARRY needs GSM_SPEC_SEG (the geometry refresh after a re-draw must be warp-uniform)"
-#endif
-
 namespace gsm {
 
 constexpr int kSpecThreads = 128;
@@ -99,8 +79,12 @@ template <> struct AdjBits<0> { typedef uint32_t type; };
 // Resident CTAs per SM the compiler must allow for.  The fp32 navigation-3 instances get 7
 // (<= 72 registers -> 28 warps/SM): at the bench batch of 16384 envs (55.4 warps per SM) that
 // is two full rounds of warps instead of 2.3 rounds at 24 warps/SM (ncu_r1_v6: 80 registers).
+#ifndef GSM_SPEC_P2_BLOCKS      // A/B: resident-CTA target of the 2-lanes-per-agent nav-3 instance
+#define GSM_SPEC_P2_BLOCKS 1
+#endif
 template <typename T, int N, int P> struct SpecMinBlocks {
-  static constexpr int value = (sizeof(T) == 4 && N == 3 && (P == 4 || P == 8)) ? 7 : 1;
+  static constexpr int value = (sizeof(T) == 4 && N == 3 && (P == 4 || P == 8)) ? 7
+                               : (sizeof(T) == 4 && N == 3 && P == 2) ? GSM_SPEC_P2_BLOCKS : 1;
 };
 
 // MODE 0: step(s).  MODE 1 (OBS): observe only.  MODE 2: steps with compiled-in auto-reset
@@ -200,10 +184,9 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   int t_now = p.t[env];
   // in-kernel auto-reset (fused rollouts only): SPEC §8 draws with the counters gsm_reset uses
   const bool auto_reset = MODE == 2 && p.auto_reset != 0;
-#if !GSM_SPEC_SEG
   int ep = auto_reset ? p.episode[env] : 0;
   const int ep0 = ep;
-#endif
+  const uint64_t genv = (uint64_t)(p.env_offset + env);
 
   // ---- per-lane output cursors (advanced by the slot strides every step) -----------------------
   const int64_t row = env * N + i;
@@ -220,7 +203,7 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   // With P == 4 lane 0 additionally walks the assign and done cursors; P < 4 walks all six.
   // (measured per variant on nav-3, P = 4: the plain MODE 0 loop is 3 % faster with lane 0 walking
   // six cursors, the auto-reset MODE 2 loop 10 % faster with 4 roles — register pressure differs)
-  constexpr bool ROLES = (P >= 8 || (P >= 4 && MODE == 2 && GSM_SPEC_ROLES_M2)) && W == 1;
+  constexpr bool ROLES = (P >= 8 || (P >= 4 && MODE == 2)) && W == 1;
   constexpr int NROLES = P >= 8 ? 6 : 4;
   unsigned char* c_role = nullptr;
   int64_t role_stride = 0;
@@ -250,88 +233,7 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     else { actx_next = ((const T*)c_act)[0]; acty_next = ((const T*)c_act)[1]; }
   }
 
-  // ---- in-kernel re-draw of finished envs (MODE 2), SPEC §8 -------------------------------------
-  // Cooperative: lane `off` of the env draws entity off (+ r * LPE in later rounds) ONCE — one
-  // Philox call site per round for the whole warp instead of one per (lane, pair) — and every
-  // consumer fetches what it needs with a shuffle over `rmask` (the ballot of the envs being
-  // re-drawn: all lanes of such an env are in it, and sources never leave their env).  The lanes
-  // that drew a landmark publish it to lm_pos right away; the agent state goes out at kernel end.
-  auto redraw = [&](const unsigned rmask, const int ep) {
-    constexpr int ROUNDS = (E + LPE - 1) / LPE;
-    const uint64_t genv = (uint64_t)(p.env_offset + env);
-    T mx = 0, my = 0, m1x = 0, m1y = 0;               // polygon / line: markers N, N + 1
-#pragma unroll
-    for (int r = 0; r < ROUNDS; r++) {
-      const int ed = r * LPE + off;
-      T qx = 0, qy = 0;
-      if (ed < E) {
-        spawn_draw<T>(genv, ep, ed, p.seed, p.ext[p.eflag[ed] >> 1], qx, qy);
-        if (ed >= N && active) { T* lp = p.lm_pos + (env * L + (ed - N)) * 2; lp[0] = qx; lp[1] = qy; }
-      }
-      if (r == 0) { px = shfl(rmask, qx, env_base + i); py = shfl(rmask, qy, env_base + i); }   // i < N <= LPE
-#pragma unroll
-      for (int c = 0; c < CH; c++) {
-        const int e = e_c[c] >= N ? e_c[c] : N;       // landmark pairs only; others fetch and drop
-        const T ax = shfl(rmask, qx, env_base + e % LPE), ay = shfl(rmask, qy, env_base + e % LPE);
-        if (e_c[c] >= N && e / LPE == r) { lmx[c] = ax; lmy[c] = ay; }
-      }
-      if (!LSA) {
-        const T ax = shfl(rmask, qx, env_base + (N + i) % LPE), ay = shfl(rmask, qy, env_base + (N + i) % LPE);
-        if ((N + i) / LPE == r) { goalx = ax; goaly = ay; }
-      } else {
-        const T ax = shfl(rmask, qx, env_base + N % LPE), ay = shfl(rmask, qy, env_base + N % LPE);
-        if (N / LPE == r) { mx = ax; my = ay; }
-        if (L > 1) {
-          const T bx = shfl(rmask, qx, env_base + (N + 1) % LPE), by = shfl(rmask, qy, env_base + (N + 1) % LPE);
-          if ((N + 1) / LPE == r) { m1x = bx; m1y = by; }
-        }
-      }
-    }
-    vx = 0; vy = 0;
-    if (LSA && off < N) {
-      if (SCN == GSM_SCN_POLYGON) {
-        slotx = mx + p.poly_r * p.slot_table[2 * off];
-        sloty = my + p.poly_r * p.slot_table[2 * off + 1];
-      } else {
-        const T f = p.slot_table[2 * off];
-        slotx = mx + f * (m1x - mx);
-        sloty = my + f * (m1y - my);
-      }
-    }
-    t_now = 0;
-  };
-
-#if GSM_SPEC_CARRY
-  // pair geometry of the CURRENT positions, per chunk: (other - me) and the rounded distance
-  T k_dx[CH], k_dy[CH], k_d[CH];
-  auto pair_geometry = [&]() {
-#pragma unroll
-    for (int c = 0; c < CH; c++) {
-      T ex = lmx[c], ey = lmy[c];
-      if (c * P < N - 1) {
-        const T ax = shfl(FULL, px, src_c[c]), ay = shfl(FULL, py, src_c[c]);
-        if (e_c[c] >= 0 && e_c[c] < N) { ex = ax; ey = ay; }
-      }
-      k_dx[c] = ex - px; k_dy[c] = ey - py;
-      k_d[c] = A::sqrt(k_dx[c] * k_dx[c] + k_dy[c] * k_dy[c]);
-    }
-  };
-  if (!OBS) pair_geometry();
-#endif
-
-#if GSM_SPEC_SEG
-  int step = 0;
-  while (step < n_steps) {
-  int seg_end = n_steps;
-  if (MODE == 2 && auto_reset) {       // steps until the first env of this warp finishes its episode
-    int left = active ? p.episode_length - t_now : 0x7fffffff;
-    left = __reduce_min_sync(FULL, left < 1 ? 1 : left);
-    seg_end = left < n_steps - step ? step + left : n_steps;
-  }
-  for (; step < seg_end; step++) {
-#else
   for (int step = 0; step < n_steps; step++) {
-#endif
     // ---- SPEC §2: action force; the next step's action is prefetched -------------------------
     T fx = 0, fy = 0;
     if (!OBS) {
@@ -352,11 +254,6 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     // ---- SPEC §3: pair forces ---------------------------------------------------------------
 #pragma unroll
     for (int c = 0; c < (OBS ? 0 : CH); c++) {
-#if GSM_SPEC_CARRY
-      if (cpair_c[c]) {
-        const T dx = -k_dx[c], dy = -k_dy[c];        // me - other: exact negation of the carried pair
-        const T dist = k_d[c];
-#else
       T qx = lmx[c], qy = lmy[c];
       if (c * P < N - 1) {                           // this chunk can hold agent pairs
         const T ax = shfl(FULL, px, src_c[c]), ay = shfl(FULL, py, src_c[c]);
@@ -365,7 +262,6 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       if (cpair_c[c]) {
         const T dx = px - qx, dy = py - qy;
         const T dist = A::sqrt(dx * dx + dy * dy);
-#endif
         const T x = A::div_const(-(dist - dmin_c[c]), p.km, p.km_inv);
         if (!(Prec<T>::kCut && x < (T)(-kFarCut))) {
           const T pen = softplus(x) * p.km;
@@ -438,9 +334,6 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       }
       const T dx = ex - px, dy = ey - py;
       const T dist = A::sqrt(dx * dx + dy * dy);
-#if GSM_SPEC_CARRY
-      k_dx[c] = dx; k_dy[c] = dy; k_d[c] = dist;
-#endif
       const bool nb = (valid_c[c] && dist < p.Rs) || goal_c[c];
       const bool col = colc_c[c] && dist < dmin_c[c];
       unsigned bits, cbits;
@@ -547,14 +440,35 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         *(int32_t*)c_asg = asg;
       }
     }
-#if !GSM_SPEC_SEG
     // ---- episode end inside a fused rollout: re-draw this env (terminal outputs stay in slot s) ----
-    if (MODE == 2) {
-      const bool need = auto_reset && t_now >= p.episode_length;
-      const unsigned rmask = __ballot_sync(FULL, need);
-      if (need) { redraw(rmask, ep); ep += 1; }
+    if (auto_reset && t_now >= p.episode_length) {
+      // cold path: everything is recomputed from (i, sub, off) and global memory here, so the
+      // per-chunk constants of the hot loop do not have to stay live for it
+      spawn_draw<T>(genv, ep, i, p.seed, p.ext[GSM_ENT_AGENT], px, py);
+      vx = 0; vy = 0;
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        const int o = c * P + sub;
+        const int e = o + (o >= i ? 1 : 0);
+        if (o < M && e >= N) spawn_draw<T>(genv, ep, e, p.seed, p.ext[p.eflag[e] >> 1], lmx[c], lmy[c]);
+      }
+      if (!LSA) spawn_draw<T>(genv, ep, N + i, p.seed, p.ext[p.eflag[N + i] >> 1], goalx, goaly);
+      if (LSA && off < N) {
+        T ax, ay, bx = 0, by = 0;
+        spawn_draw<T>(genv, ep, N, p.seed, p.ext[p.eflag[N] >> 1], ax, ay);
+        if (L > 1) spawn_draw<T>(genv, ep, N + 1, p.seed, p.ext[p.eflag[N + 1] >> 1], bx, by);
+        if (SCN == GSM_SCN_POLYGON) {
+          slotx = ax + p.poly_r * p.slot_table[2 * off];
+          sloty = ay + p.poly_r * p.slot_table[2 * off + 1];
+        } else {
+          const T f = p.slot_table[2 * off];
+          slotx = ax + f * (bx - ax);
+          sloty = ay + f * (by - ay);
+        }
+      }
+      t_now = 0;
+      ep += 1;
     }
-#endif
     // advance the cursors to the next slot of the rollout buffers
     c_idx += ss.nbr_idx; c_feat += ss.nbr_feat; c_obs += ss.obs;
     if (ROLES) {
@@ -565,27 +479,6 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       c_asg += ss.assign; c_done += ss.done;
     }
   }
-#if GSM_SPEC_SEG
-  // ---- between segments: re-draw the envs that just finished (terminal outputs stay in their slot).
-  // Nothing of this block is live across the hot loop: the episode counter and the landmark
-  // positions go through global memory, everything else is recomputed from the lane index.
-  if (MODE == 2) {
-    const bool need = auto_reset && t_now >= p.episode_length;
-    const unsigned rmask = __ballot_sync(FULL, need);
-    if (need) {
-      const int ep = p.episode[env];
-      __syncwarp(rmask);                               // every lane of the env has read ep before lane 0 bumps it
-      redraw(rmask, ep);
-      if (off == 0 && active) p.episode[env] = ep + 1;
-#if GSM_SPEC_CARRY
-    }
-    if (rmask != 0 && !OBS) {                          // warp-uniform: the geometry pass shuffles with FULL mask
-      pair_geometry();
-#endif
-    }
-  }
-  }
-#endif
 
   // ---- state back to HBM ------------------------------------------------------------------------
   if (!OBS && sub == 0 && active) {
@@ -593,9 +486,15 @@ env_steps_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     st2<T>(a, px, py); st2<T>(a + 2, vx, vy);
     if (i == 0) p.t[env] = t_now;
   }
-#if !GSM_SPEC_SEG
-  if (auto_reset && ep != ep0 && active && off == 0) p.episode[env] = ep;   // landmarks were published at the re-draw
-#endif
+  if (auto_reset && ep != ep0 && active) {             // the landmarks of the last re-draw + episode count
+    for (int l = off; l < L; l += LPE) {
+      T x, y;
+      spawn_draw<T>(genv, ep - 1, N + l, p.seed, p.ext[p.eflag[N + l] >> 1], x, y);
+      T* lp = p.lm_pos + (env * L + l) * 2;
+      lp[0] = x; lp[1] = y;
+    }
+    if (off == 0) p.episode[env] = ep;
+  }
 }
 
 }  // namespace gsm

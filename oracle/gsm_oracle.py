@@ -37,6 +37,8 @@ def lib() -> C.CDLL:
                                                          C.c_void_p, iop]
             getattr(_lib, f"orc_observe_{sfx}").argtypes = [cfgp, C.c_int64, C.c_void_p,
                                                             C.c_void_p, C.c_void_p, iop]
+            getattr(_lib, f"orc_evaluate_{sfx}").argtypes = [cfgp, C.c_int64, C.c_void_p,
+                                                             C.c_void_p, C.c_void_p, iop]
             getattr(_lib, f"orc_reset_{sfx}").argtypes = [cfgp, C.c_int64, C.c_int64, C.c_uint64,
                                                           C.c_void_p, C.c_int64, C.c_void_p,
                                                           C.c_void_p, C.c_void_p, C.c_void_p]
@@ -119,6 +121,15 @@ class OracleEnv:
         bufs = self.alloc_io() if bufs is None else bufs
         io = self._io_struct(bufs)
         getattr(lib(), f"orc_observe_{self._sfx}")(
+            C.byref(self._c), self.n_envs, self.agent_state.ctypes.data,
+            self.landmark_pos.ctypes.data, self.step_count.ctypes.data, C.byref(io))
+        return bufs
+
+    def evaluate(self, bufs: dict | None = None) -> dict:
+        """SPEC §5-7 of the current state INCLUDING reward / cost / done (observe() leaves those)."""
+        bufs = self.alloc_io() if bufs is None else bufs
+        io = self._io_struct(bufs)
+        getattr(lib(), f"orc_evaluate_{self._sfx}")(
             C.byref(self._c), self.n_envs, self.agent_state.ctypes.data,
             self.landmark_pos.ctypes.data, self.step_count.ctypes.data, C.byref(io))
         return bufs

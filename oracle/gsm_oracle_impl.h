@@ -238,12 +238,22 @@ static void ORC(range)(int64_t lo, int64_t hi, void* ctx) {
   for (int64_t env = lo; env < hi; env++) {
     REAL* ag = jb->ag + env * N * 4;
     const REAL* lm = jb->lm + env * L * 2;
-    if (jb->physics) {
+    if (jb->physics == 1) {
       ORC(physics_env)(jb->c, ag, lm, jb->io->actions, env);
       jb->t[env] += 1;
     }
-    ORC(observe_env)(jb->c, ag, lm, jb->t[env], env, jb->io, jb->physics);
+    ORC(observe_env)(jb->c, ag, lm, jb->t[env], env, jb->io, jb->physics != 0);
   }
+}
+
+/* SPEC §5-7 (observation, graph, assignment, reward, cost, done) of a GIVEN state, no physics:
+ * what tools/unblock.py uses to check the scenario callbacks on the reference's own post-step
+ * states, independently of whether the physics sections agree. */
+int ORC(evaluate)(const orc_config* c, int64_t n_envs, const REAL* agent_state, const REAL* lm_pos,
+                  const int32_t* step_count, const orc_step_io* io) {
+  ORC(job) jb = {c, (REAL*)agent_state, lm_pos, (int32_t*)step_count, io, 2};
+  orc_parallel_for(n_envs, ORC(range), &jb);
+  return 0;
 }
 
 int ORC(step)(const orc_config* c, int64_t n_envs, REAL* agent_state, const REAL* lm_pos,

@@ -61,16 +61,18 @@ def main():
     res = {}
     for v in args.variants.split(","):
         name, *kvs = v.split(":")
-        env = dict(os.environ)
+        env, streams = dict(os.environ), args.streams
         for kv in kvs:
             k, val = kv.split("=", 1)
             if k == "lib":
                 env["GSM_LIB_PATH"] = os.path.join(ROOT, val)
+            elif k == "streams":
+                streams = int(val)
             else:
                 env[k] = val
         cmd = [sys.executable, os.path.abspath(__file__), "--child", "--scenario", args.scenario, "--agents",
                str(args.agents), "--envs", str(args.envs), "--T", str(args.T), "--K", str(args.K), "--streams",
-               str(args.streams), "--ms", str(args.ms)]
+               str(streams), "--ms", str(args.ms)]
         p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
         line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT ")]
         res[name] = json.loads(line[0][7:]) if line else {"error": (p.stderr or p.stdout)[-400:]}

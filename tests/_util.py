@@ -89,3 +89,43 @@ def near_threshold_rows(cfg, agent_state, landmark_pos, eps):
     for i in range(N):
         near[:, i, i] = False
     return near.any(-1)
+
+
+# ---- reference-recorded goldens (tools/unblock.py) ----------------------------------------------
+def ref_golden_files(tmp_factory=None):
+    """Trajectory files in the unblock kit's format.  GSM_REF_GOLDEN_DIR (set by `tools/unblock.py
+    --pytest` once the real gsmarl/ sources are mounted) wins; without it the files are recorded
+    here and now from the SYNTHETIC stand-in tree of tools/fake_gsmarl.py — an implementation of
+    SPEC.md that shares no code with the product or the oracle — so the replay path itself is
+    always exercised."""
+    import subprocess
+    import sys
+    d = os.environ.get("GSM_REF_GOLDEN_DIR")
+    if not d:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        base = str(tmp_factory.mktemp("refgold"))
+        sys.path.insert(0, os.path.join(root, "tools"))
+        import fake_gsmarl
+        fake_gsmarl.write_tree(os.path.join(base, "ref"))
+        subprocess.run([sys.executable, os.path.join(root, "tools", "unblock.py"), "--ref", os.path.join(base, "ref"),
+                        "--out", os.path.join(base, "out"), "--configs", "nav-3,nav-6,polygon-6,line-6"],
+                       check=True, capture_output=True, timeout=600)
+        d = os.path.join(base, "out", "goldens")
+    return sorted(glob.glob(os.path.join(d, "ref_*.npz")))
+
+
+def load_ref_golden(path):
+    """(recording dict, field dict of the world it was recorded in) of one ref_*.npz."""
+    import json
+    z = np.load(path)
+    return {k: z[k] for k in z.files if k != "world_json"}, json.loads(str(z["world_json"]))
+
+
+def ref_world_pair(fields, dtype="f64"):
+    """The product WorldConfig and the oracle World of a recorded reference world (continuous
+    controls: the recording stores the force each action produced, SPEC §2)."""
+    from gs_marl_b200.config import WorldConfig
+    f = dict(fields, dtype=dtype, action_mode="continuous")
+    f["discrete_u"] = [tuple(u) for u in f["discrete_u"]]
+    slot = oracle_worlds.spec_slot_table(f["scenario"], f["n_agents"])
+    return WorldConfig(slot_table=slot, **f), oracle_worlds.World(slot_table=slot, **f)
