@@ -72,6 +72,8 @@ struct gsm_env {
   cudaGraphExec_t graph_exec = nullptr;
   int graph_steps = 0;
   gsm_step_io graph_io;
+  uint64_t graph_seed = 0;       // the captured reset_kernel launches carry the seed BY VALUE
+  int graph_auto_reset = 0;
   int64_t launches = 0;
   uint64_t seed = 0;
   int auto_reset = 0;      // gsm_set_auto_reset: applies inside gsm_rollout only
@@ -282,7 +284,11 @@ int copy_out(gsm_env* h, const gsm_step_io& host_io, bool with_rcd) {
 
 struct DeviceGuard {
   int prev = -1;
-  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess; else prev = -1;
+  }
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
@@ -471,7 +477,8 @@ int gsm_rollout(gsm_env* h, int32_t n_steps, const gsm_step_io* io, void* stream
     if (r != -1000) return r;
   }
   if (h->auto_reset && !io->done) return fail(h, GSM_ERR_INVALID_ARG, "auto-reset rollout needs io.done");
-  const bool hit = h->graph_exec && h->graph_steps == n_steps &&
+  const bool hit = h->graph_exec && h->graph_steps == n_steps && h->graph_seed == h->seed &&
+                   h->graph_auto_reset == h->auto_reset &&
                    std::memcmp(&h->graph_io, io, sizeof(gsm_step_io)) == 0;
   if (!hit) {
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
@@ -501,6 +508,8 @@ int gsm_rollout(gsm_env* h, int32_t n_steps, const gsm_step_io* io, void* stream
     if (ce != cudaSuccess) return cuda_fail(h, (int)ce, "cudaGraphInstantiate");
     h->graph_steps = n_steps;
     h->graph_io = *io;
+    h->graph_seed = h->seed;
+    h->graph_auto_reset = h->auto_reset;
   }
   GSM_CUDA(h, cudaGraphLaunch(h->graph_exec, (cudaStream_t)stream));
   h->launches += (int64_t)n_steps * (h->auto_reset ? 3 : 1);
@@ -560,6 +569,8 @@ int gsm_reset_host(gsm_env* h, uint64_t seed, const uint8_t* mask, int64_t mask_
   int st = ensure_host_path(h);
   if (st) return st;
   const uint8_t* dmask = nullptr;
+  if (mask && io && any_obs_output(*io) && !is_arena_io(h, *io))
+    return fail(h, GSM_ERR_UNSUPPORTED, "masked gsm_reset_host needs the gsm_host_io buffers (partial rows are kept on the device copy)");
   if (mask) {
     if (mask_stride < 1 || mask_stride > h->hp.N) return fail(h, GSM_ERR_INVALID_ARG, "host mask_stride must be in [1, N]");
     GSM_CUDA(h, cudaMemcpyAsync(h->d_mask, mask, (size_t)(h->hp.n_envs - 1) * mask_stride + 1,
@@ -567,11 +578,11 @@ int gsm_reset_host(gsm_env* h, uint64_t seed, const uint8_t* mask, int64_t mask_
     dmask = h->d_mask;
   }
   const bool want = io && any_obs_output(*io);
+  if (want && mask && !is_arena_io(h, *io))      // checked BEFORE anything is mutated: an error call has no side effect
+    return fail(h, GSM_ERR_UNSUPPORTED, "masked gsm_reset_host needs the gsm_host_io buffers (partial rows are kept on the device copy)");
   st = gsm_reset(h, seed, dmask, mask_stride, want ? &h->d_io : nullptr, h->stream);
   if (st) return st;
   if (!want) { GSM_CUDA(h, cudaStreamSynchronize(h->stream)); return GSM_OK; }
-  if (mask && !is_arena_io(h, *io))
-    return fail(h, GSM_ERR_UNSUPPORTED, "masked gsm_reset_host needs the gsm_host_io buffers (partial rows are kept on the device copy)");
   return copy_out(h, *io, false);
 }
 
@@ -676,7 +687,9 @@ int gsm_lsa(const void* cost, int32_t* col4row, int64_t n_problems, int32_t n, i
     cudaGetLastError();
     return fail(nullptr, GSM_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
   }
+  if (device < 0 || device >= ndev) return fail(nullptr, GSM_ERR_INVALID_ARG, "gsm_lsa: device index out of range");
   DeviceGuard guard(device);
+  if (!guard.ok) return fail(nullptr, GSM_ERR_CUDA, "gsm_lsa: cudaSetDevice failed");
   const int e = dtype == GSM_F32 ? gsm::launch_lsa_f32(cost, col4row, n_problems, n, (cudaStream_t)stream)
                                  : gsm::launch_lsa_f64(cost, col4row, n_problems, n, (cudaStream_t)stream);
   if (e) return cuda_fail(nullptr, e, "lsa kernel launch");

@@ -11,21 +11,23 @@
 //   z   = W_h [e ; sum_r a_r m_r] + b_h                     [n_actions] logits
 //   action = argmax_k (z_k + Gumbel_k),  Gumbel from Philox4x32-10 keyed like the env resets.
 //
-// Design for sm_100a: one thread per agent row, no shuffles, shared memory only for the 128-entry
-// sort below.  The weights ride in the kernel PARAMETER space (9.5 KB, __grid_constant__): the
-// 64-wide hidden loops are fully unrolled, so every weight has an immediate constant-bank offset,
-// ptxas fetches four at a time with LDCU.128 into uniform registers and the FFMAs take them as
-// uniform-register operands — no weight ever goes through a load/store unit.  (Partially unrolled
-// loops with a uniform-register INDEX into the constant bank measured 4x slower; packed FFMA2
-// variants did not pay either: profiles/README.md, profiles/fma_peak.cu.)  The head is linear, so
-// W_h's neighbour half is applied to every row's m_r on the fly (hr = W_h[:, H:] m_r) and the
-// softmax is the online (running max / running sum) form over 1 + n_actions accumulators: a row
-// costs 64 x 13 FFMA-class instructions and nothing of size H is ever stored.  Only the cnt valid
-// rows are visited; the padded rows the env kernel zero-fills are never read.  Bound: fp32 issue
-// slots (17.25 per 13 FFMA; 88.7 % issue-active at 786k rows), not HBM (220 B per agent in, 8 B out).
+// Design for sm_100a (details in front of graph_actor_kernel below): a block owns 128 agents; the
+// ego branch runs as packed FFMA2 over agent pairs, the block's VALID neighbour rows are flattened
+// into one list of work items processed two per thread as packed FFMA2 (no divergence on the
+// per-agent row count), and a per-agent online softmax folds the parked row results.  The weights
+// ride in the kernel PARAMETER space (9.5 KB, __grid_constant__): the 64-wide hidden loops are fully
+// unrolled, every weight has an immediate constant-bank offset, ptxas fetches four at a time with
+// LDCU.128 into uniform registers and the FFMA2s take them as the broadcast uniform-scalar operand —
+// no weight ever goes through a load/store unit.  The head is linear, so W_h's neighbour half is
+// applied to every row's m_r on the fly (hr = W_h[:, H:] m_r): nothing of size H is ever stored.
+// Only the cnt valid rows are visited; the padded rows the env kernel zero-fills are never read.
+// Bound: fp32 issue / FMA pipe (54 % of the measured 72 TFLOP/s FFMA peak at 786k rows), not HBM
+// (220 B per agent in, 8 B out).  History of the rejected forms (thread per agent, hidden-unit pair
+// packing, shared-memory weights with rolled loops): profiles/README.md, profiles/rejected/.
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 
 #include "../../include/gsmarl_b200.h"
@@ -249,7 +251,8 @@ graph_actor_kernel(const __grid_constant__ PolicyParams w, const __grid_constant
       for (int q = 0; q < 4; q++) {
         const int a = 4 * b + q;
         if (a < NA) {
-          const float u = ((float)(r[q] >> 8) + 0.5f) * 5.9604644775390625e-8f;   // (0, 1)
+          // 23 random bits + half a step: every value k * 2^-23 + 2^-24 is exact in fp32 and lies in (0, 1)
+          const float u = (float)(r[q] >> 9) * 1.1920928955078125e-7f + 5.9604644775390625e-8f;
           const float v = z[a] - logf(-logf(u));
           if (a == 0 || v > bv) { bv = v; best = a; zb = z[a]; }
         }
@@ -340,9 +343,27 @@ int pack(const gsm_policy_weights* w, gsm::PolicyParams* p) {
 }
 struct DevGuard {
   int prev = -1;
-  explicit DevGuard(int d) { cudaGetDevice(&prev); if (d != prev) cudaSetDevice(d); }
+  bool ok = true;
+  explicit DevGuard(int d) {
+    cudaGetDevice(&prev);
+    if (d != prev) ok = cudaSetDevice(d) == cudaSuccess;
+  }
   ~DevGuard() { int cur; cudaGetDevice(&cur); if (cur != prev && prev >= 0) cudaSetDevice(prev); }
 };
+// 0 <= device < device count, as gsm_create checks; GSM_OK or the error status to return.
+int check_device(int device, const char* who) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return pfail(GSM_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) {
+    static thread_local char msg[96];
+    snprintf(msg, sizeof(msg), "%s: device index out of range", who);
+    return pfail(GSM_ERR_INVALID_ARG, msg);
+  }
+  return GSM_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -357,12 +378,9 @@ int gsm_policy_act(const gsm_policy_weights* w, const gsm_policy_io* io, int dev
     return pfail(GSM_ERR_INVALID_ARG, "gsm_policy_act: obs, nbr_feat, nbr_cnt and actions are required");
   if (io->n_rows < 0 || io->max_nbrs < 1) return pfail(GSM_ERR_INVALID_ARG, "gsm_policy_act: bad n_rows / max_nbrs");
   if (io->n_rows > ((int64_t)1 << 31) * 128 - 128) return pfail(GSM_ERR_INVALID_ARG, "gsm_policy_act: n_rows too large");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    cudaGetLastError();
-    return pfail(GSM_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
-  }
+  if (const int ds = check_device(device, "gsm_policy_act")) return ds;
   DevGuard guard(device);
+  if (!guard.ok) return pfail(GSM_ERR_CUDA, "gsm_policy_act: cudaSetDevice failed");
   gsm::PolicyIO k;
   k.obs = io->obs; k.nbr_feat = io->nbr_feat; k.nbr_cnt = io->nbr_cnt;
   k.actions = io->actions; k.logp = io->logp; k.logits = io->logits; k.values = io->values;
@@ -379,13 +397,10 @@ int gsm_gae(const float* reward, const float* cost, const float* values, const u
   if (!reward || !cost || !values || !done || !returns)
     return pfail(GSM_ERR_INVALID_ARG, "gsm_gae: reward, cost, values, done and returns are required");
   if (n_steps < 1 || n_rows < 0 || slot_rows < n_rows) return pfail(GSM_ERR_INVALID_ARG, "gsm_gae: bad sizes");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    cudaGetLastError();
-    return pfail(GSM_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
-  }
+  if (const int ds = check_device(device, "gsm_gae")) return ds;
   if (n_rows == 0) return GSM_OK;
   DevGuard guard(device);
+  if (!guard.ok) return pfail(GSM_ERR_CUDA, "gsm_gae: cudaSetDevice failed");
   gsm::GaeParams p{reward, cost, values, done, returns, advantages, n_rows, slot_rows, n_steps, gamma, lam};
   const int64_t threads = n_rows * GSM_POLICY_VALUE_HEADS;
   gsm::gae_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);

@@ -68,7 +68,7 @@ def forward(w, obs, nbr_feat, nbr_cnt, dtype=np.float64):
 
 def gumbel(n_rows, n_actions, seed, step, row_offset=0):
     """fp32 Gumbel noise the kernel adds: Philox block b covers actions 4b..4b+3; counter
-    (row lo, row hi, step, 0x80000000 | b), key (seed lo, seed hi); u = ((x >> 8) + 0.5) * 2^-24."""
+    (row lo, row hi, step, 0x80000000 | b), key (seed lo, seed hi); u = (x >> 9) * 2^-23 + 2^-24 (exact in fp32, inside (0, 1))."""
     g = np.uint64(row_offset) + np.arange(n_rows, dtype=np.uint64)
     out = np.empty((n_rows, n_actions), dtype=np.float32)
     for b in range((n_actions + 3) // 4):
@@ -77,7 +77,7 @@ def gumbel(n_rows, n_actions, seed, step, row_offset=0):
         for q in range(4):
             a = 4 * b + q
             if a < n_actions:
-                u = ((r[q] >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -24)
+                u = (r[q] >> np.uint32(9)).astype(np.float32) * np.float32(2.0 ** -23) + np.float32(2.0 ** -24)
                 out[:, a] = -np.log(-np.log(u))
     return out
 

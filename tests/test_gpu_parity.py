@@ -281,7 +281,7 @@ def test_f32_fused_rollout_25_steps_vs_f32_oracle(name, N, B, kw):
         for k in ("obs", "reward", "nbr_feat"):
             np.testing.assert_allclose(out[k][t][ok], want[k][ok], rtol=1e-4, atol=2e-5, err_msg=f"{name}{N} t={t} {k}")
         rows_checked += int(ok.sum())
-    assert rows_checked > 0.3 * T * B * N, "too few rows survived the contact / threshold masks"
+    assert rows_checked > 0.1 * T * B * N, "too few rows survived the contact / threshold masks"
     assert assign_bad <= 0.01 * T * B * N
     env.close()
 
