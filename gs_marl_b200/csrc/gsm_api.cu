@@ -377,6 +377,11 @@ int gsm_create(const gsm_config* cfg, int64_t n_envs, int64_t env_offset, int de
     if (cudaMemcpy(p, fl.data(), E, cudaMemcpyHostToDevice) != cudaSuccess)
       return bail(fail(h, GSM_ERR_CUDA, "upload eflag"));
     hp.eflag = (const uint8_t*)p;
+    hp.h_consts = (E <= gsm::kHostConstE && N <= gsm::kHostConstN) ? 1 : 0;
+    if (hp.h_consts) {
+      for (int e = 0; e < E; e++) { hp.h_size[e] = cfg->size[e]; hp.h_eflag[e] = fl[e]; }
+      for (int i = 0; i < N; i++) { hp.h_mass[i] = cfg->mass[i]; hp.h_accel[i] = cfg->accel[i]; hp.h_maxsp[i] = cfg->max_speed[i]; }
+    }
   }
   if ((st = dev_alloc(h, sz.agent_state, &p))) return bail(st); hp.agent_state = p;
   if ((st = dev_alloc(h, sz.landmark_pos ? sz.landmark_pos : 16, &p))) return bail(st); hp.lm_pos = p;

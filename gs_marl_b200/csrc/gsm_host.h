@@ -22,7 +22,13 @@ struct HostParams {
   void* agent_state; void* lm_pos; int32_t* t; int32_t* episode;
   int auto_reset;        // set per launch by the API layer (only gsm_rollout turns it on)
   uint64_t seed;         // seed of the handle's last reset
+  // host copies of the per-entity constants for kernels that take them in the parameter space
+  // (gsm_kernels_wide.cuh); h_consts = 1 when E <= kHostConstE and N <= kHostConstN
+  int h_consts;
+  double h_size[32], h_mass[8], h_accel[8], h_maxsp[8];
+  int32_t h_eflag[32];
 };
+constexpr int kHostConstE = 32, kHostConstN = 8;
 
 struct RolloutStrides {  // bytes between consecutive steps of each rollout buffer
   int64_t actions, obs, nbr_idx, nbr_feat, nbr_cnt, adj, reward, cost, done, assign;

@@ -3,6 +3,7 @@
 #include "gsm_kernels_big.cuh"
 #include "gsm_kernels_lane.cuh"
 #include "gsm_kernels_team.cuh"
+#include "gsm_kernels_wide.cuh"
 #define GSM_REAL double
 #define GSM_SFX(name) name##_f64
 #include "gsm_launch.inl"

@@ -179,6 +179,47 @@ static int launch_spec_one(const KParams<GSM_REAL>& kp, int n_steps, const StepS
   return (int)cudaGetLastError();
 }
 
+// ---- one-lane-per-other navigation kernel (gsm_kernels_wide.cuh) ---------------------------------
+// (N, L) instances; preferred over the (N*P lanes per env) specialised kernel where one exists.
+#define GSM_WIDE_TABLE(X) X(3, 6)
+
+static bool has_wide(const HostParams& hp) {
+  if (!spec_enabled() || env_int("GSM_NO_WIDE", 0) != 0 || env_int("GSM_SPEC_P", 0) != 0) return false;
+  if (hp.scenario != GSM_SCN_NAVIGATION || !hp.h_consts) return false;
+  // 32-bit lane offsets into one slot of the largest output
+  if (hp.n_envs * hp.N * hp.K * (int64_t)(GSM_NBR_FEAT_DIM * sizeof(GSM_REAL)) >= (1ll << 31)) return false;
+#define X(n, l) if (hp.N == n && hp.L == l) return true;
+  GSM_WIDE_TABLE(X)
+#undef X
+  return false;
+}
+
+template <int N, int L>
+static int launch_wide_one(const HostParams& hp, const KParams<GSM_REAL>& kp, int n_steps, const StepStrides& ss,
+                           bool observe, cudaStream_t st) {
+  typedef GSM_REAL T;
+  constexpr int E = N + L, EPW = 32 / wide_pow2(E - 1), WPC = kWideThreads / 32;
+  WideConsts<T, N, E> wc;
+  for (int e = 0; e < E; e++) { wc.size[e] = (T)hp.h_size[e]; wc.eflag[e] = hp.h_eflag[e]; }
+  for (int i = 0; i < N; i++) {
+    wc.mass[i] = (T)hp.h_mass[i]; wc.mass_inv[i] = (T)1 / (T)hp.h_mass[i];
+    wc.accel[i] = (T)hp.h_accel[i]; wc.maxsp[i] = (T)hp.h_maxsp[i];
+  }
+  const int64_t grid = (kp.n_envs + EPW * WPC - 1) / (EPW * WPC);
+  const size_t smem = wide_smem_bytes((int)sizeof(T), N, kp.K, EPW);
+  auto k = observe ? env_wide_kernel<T, N, L, 1> : (kp.auto_reset ? env_wide_kernel<T, N, L, 2> : env_wide_kernel<T, N, L, 0>);
+  static bool attr_done[3] = {false, false, false};      // per instance (this function is one per (T, N, L))
+  const int which = observe ? 1 : (kp.auto_reset ? 2 : 0);
+  if (!attr_done[which]) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem > 48 * 1024 ? (int)smem : 48 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    attr_done[which] = true;
+  }
+  k<<<(unsigned)grid, kWideThreads, smem, st>>>(kp, observe ? 1 : n_steps, ss, wc);
+  return (int)cudaGetLastError();
+}
+
 int GSM_SFX(launch_spec)(const HostParams& hp, const gsm_step_io& io, int n_steps,
                          const RolloutStrides& rs, int observe, const uint8_t* mask,
                          int64_t mask_stride, cudaStream_t st) {
@@ -191,6 +232,11 @@ int GSM_SFX(launch_spec)(const HostParams& hp, const gsm_step_io& io, int n_step
   ss.actions = rs.actions; ss.obs = rs.obs; ss.nbr_idx = rs.nbr_idx; ss.nbr_feat = rs.nbr_feat;
   ss.nbr_cnt = rs.nbr_cnt; ss.adj = rs.adj; ss.reward = rs.reward; ss.cost = rs.cost;
   ss.done = rs.done; ss.assign = rs.assign;
+  if (has_wide(hp)) {
+#define X(n, l) if (hp.N == n && hp.L == l) return launch_wide_one<n, l>(hp, kp, n_steps, ss, observe != 0, st);
+    GSM_WIDE_TABLE(X)
+#undef X
+  }
 #define X(S, n, l, pp) \
   if (hp.scenario == S && hp.N == n && hp.L == l && P == pp) return launch_spec_one<S, n, l, pp>(kp, n_steps, ss, observe != 0, st);
   GSM_SPEC_TABLE(X)
