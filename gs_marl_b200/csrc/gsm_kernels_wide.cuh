@@ -51,21 +51,46 @@ __device__ __forceinline__ double softplus1(double x) { return fmax(x, 0.0) + r_
 template <typename T>
 __device__ __forceinline__ T shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-// Shared-memory staging of one warp-step's rows: EPW envs' nbr_feat, nbr_idx and obs blocks are three
-// contiguous, 16-byte aligned regions of the slot (env-major layout), so the rows are written with STS
-// and leave as three bulk copies (cp.async.bulk.global.shared::cta, UBLKCP) issued by one lane — no
-// per-lane 24-byte global stores, no L1TEX sector inflation.  Two buffers per warp: the copies of step s
-// drain while step s+1 is computed.
-__host__ __device__ constexpr size_t wide_stage_bytes(int rb, int N, int K, int EPW) {
-  return (size_t)EPW * N * K * (GSM_NBR_FEAT_DIM * rb + 4) + (size_t)EPW * N * GSM_OBS_DIM * rb;
+// Shared memory per warp:
+//   * entity table [EPW envs][E] of (x, y, vx, vy): lane a < N owns agent a — it alone integrates it and
+//     publishes it with one 16-byte store; every chunk reads agent i and "its other" with two 16-byte
+//     loads.  No per-lane copies of all agents, no select chains, no position shuffles.
+//   * two staging buffers [feat][idx][obs][cnt][adj][assign][reward][cost]: one warp-step's outputs are
+//     eight contiguous, 16-byte aligned regions of the slot (env-major layout).  Rows are written with
+//     STS; the feature block (77 % of the bytes) leaves as ONE bulk copy (cp.async.bulk.global.shared::cta,
+//     UBLKCP) issued by one lane, the small blocks as coalesced 16-byte LDS + STG by a few lanes each.
+//     The copies of step s drain while step s+1 is computed.
+template <typename T> struct __align__(16) WideEnt { T x, y, vx, vy; };
+
+struct WideSmem {              // byte offsets inside one staging buffer / one warp's block
+  unsigned feat, idx, obs, cnt, adj, cost, rew, asg, buf;   // region offsets, buffer size
+  unsigned ent, warp;                                         // entity table offset, bytes per warp
+};
+__host__ __device__ inline WideSmem wide_smem_layout(int rb, int N, int E, int K, int EPW) {
+  WideSmem w;
+  unsigned o = 0;
+  w.feat = o; o += (unsigned)(EPW * N * K * GSM_NBR_FEAT_DIM * rb);
+  w.idx = o; o += (unsigned)(EPW * N * K * 4);
+  w.obs = o; o += (unsigned)(EPW * N * GSM_OBS_DIM * rb);
+  w.cnt = o; o += (unsigned)(EPW * N * 4);
+  w.adj = o; o += (unsigned)(EPW * N * 4);
+  w.cost = o; o += (unsigned)(EPW * N * rb);
+  w.rew = o; o += (unsigned)(EPW * N * rb);
+  w.asg = o; o += (unsigned)(EPW * N * 4);
+  w.buf = (o + 15u) & ~15u;
+  w.ent = 2 * w.buf;
+  w.warp = w.ent + (unsigned)(EPW * E * 4 * rb);
+  return w;
 }
-__host__ __device__ constexpr size_t wide_smem_bytes(int rb, int N, int K, int EPW) {
-  return 2 * (kWideThreads / 32) * wide_stage_bytes(rb, N, K, EPW);
+__host__ __device__ inline size_t wide_smem_bytes(int rb, int N, int E, int K, int EPW) {
+  return (size_t)(kWideThreads / 32) * wide_smem_layout(rb, N, E, K, EPW).warp;
 }
 
 // MODE 0: step(s).  MODE 1: observe only (reset path, optional per-env mask).  MODE 2: steps with
-// in-kernel auto-reset.  Needs every output pointer non-NULL and n_envs * N * K * 6 * sizeof(T) < 2^31
-// (32-bit lane offsets against warp-uniform 64-bit slot bases); the launcher checks both.
+// in-kernel auto-reset.  The launcher checks what the kernel assumes: every output pointer non-NULL;
+// all agents share one size and one collide flag (the pair constants of a lane are then the same in
+// every chunk); n_envs * N * K * 6 * sizeof(T) < 2^31 (32-bit offsets against 64-bit slot bases); in
+// fp32 the five 4-byte-per-agent outputs share one slot stride.
 template <typename T, int N, int L, int MODE>
 __global__ void __launch_bounds__(kWideThreads, WideMinBlocks<T>::value)
 env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
@@ -74,106 +99,103 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   constexpr int E = N + L, M = E - 1, GW = wide_pow2(M), EPW = 32 / GW;
   constexpr bool OBS = MODE == 1;
   constexpr unsigned FULL = 0xffffffffu;
+  constexpr int RB = (int)sizeof(T);
+  constexpr int RS4 = EPW * N * 4, RST = EPW * N * RB;      // bytes of a per-agent 4-byte / real block of the warp
+  constexpr int PC4 = RS4 / 16, PCT = RST / 16, NPIECE = 3 * PC4 + 2 * PCT;
   static_assert(GW <= 32 && E <= 32, "an env must fit in one warp, adjacency in one word");
-  static_assert(L >= N && 2 * N <= GW, "navigation: goal i is landmark i; obs roles need 2N lanes");
-  static_assert(N <= 8, "per-chunk flag bits");
+  static_assert(L >= N && 2 * N <= GW + 1 && N >= 3, "goal i is landmark i, held by lane N-1+i; lanes 0..2 stage scalars");
+  static_assert(RS4 % 16 == 0 && NPIECE <= 32, "per-warp scalar blocks leave in 16-byte pieces, one per lane");
+  static_assert(EPW * N * M * 4 / 16 <= 64 && EPW * N * GSM_OBS_DIM * RB / 16 <= 64, "idx / obs blocks leave in <= 2 passes");
   typedef Arith<T> A;
+  typedef WideEnt<T> Ent;
+  typedef float4 V;                                        // a 16-byte piece
   extern __shared__ __align__(128) unsigned char wsm[];
   const int K = p.K;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane / GW, j = lane % GW, shift = grp * GW;
-  const int64_t env_w0 = ((int64_t)blockIdx.x * (kWideThreads / 32) + warp) * EPW;
-  const int64_t env_raw = env_w0 + grp;
-  bool active = env_raw < p.n_envs;
-  if (OBS && p.mask != nullptr && active) active = p.mask[env_raw * p.mask_stride] != 0;
-  const int env = active ? (int)env_raw : 0;           // idle groups shadow env 0, never store
+  const int env_w0 = (int)(((int64_t)blockIdx.x * (kWideThreads / 32) + warp) * EPW);
+  bool active = env_w0 + grp < p.n_envs;
+  if (OBS && p.mask != nullptr && active) active = p.mask[(int64_t)(env_w0 + grp) * p.mask_stride] != 0;
+  const int env = active ? env_w0 + grp : 0;            // idle groups shadow env 0, never store
   const bool has = M == GW ? true : j < M;
-  const bool is_lm = j >= N - 1;                        // my other is landmark j + 1 - N in every chunk
-  const unsigned below = low_mask(j);
+  const bool own = j < N;                               // I own (integrate, publish) agent j
+  const int ja = own ? j : 0;
   const unsigned act_bits = __ballot_sync(FULL, active);
+  const WideSmem lay = wide_smem_layout(RB, N, E, K, EPW);
   // staged bulk path: the warp's EPW envs all exist (and are unmasked) and every slot is 16-byte aligned
   const bool bulk = act_bits == FULL &&
-      ((((uintptr_t)p.obs | (uintptr_t)p.nbr_idx | (uintptr_t)p.nbr_feat | (uintptr_t)ss.obs |
-         (uintptr_t)ss.nbr_idx | (uintptr_t)ss.nbr_feat) & 15) == 0);
+      ((((uintptr_t)p.obs | (uintptr_t)p.nbr_idx | (uintptr_t)p.nbr_feat | (uintptr_t)p.nbr_cnt | (uintptr_t)p.adj |
+         (uintptr_t)p.assign | (uintptr_t)p.reward | (uintptr_t)p.cost | (uintptr_t)ss.obs | (uintptr_t)ss.nbr_idx |
+         (uintptr_t)ss.nbr_feat | (uintptr_t)ss.nbr_cnt | (uintptr_t)ss.adj | (uintptr_t)ss.assign |
+         (uintptr_t)ss.reward | (uintptr_t)ss.cost) & 15) == 0);
 
-  // ---- lane constants: one flag word (bit i: contact pair in chunk i, 8+i: counts as collision,
-  //      16+i: agent i's own goal and own_goal_always), the size and type of my landmark ----------------
-  unsigned cfl = 0;
-#pragma unroll
-  for (int i = 0; i < N; i++) {
-    const int e = has ? j + (j >= i ? 1 : 0) : 0;
-    const int fl = wc.eflag[e];
-    if (has && (wc.eflag[i] & 1) && (fl & 1)) cfl |= 1u << i;
-    if (has && (e < N || (p.cost_obstacles && (fl >> 1) == GSM_ENT_OBSTACLE))) cfl |= 1u << (8 + i);
-    if (has && p.own_goal_always && e == N + i) cfl |= 1u << (16 + i);
-  }
-  const T size_lm = wc.size[has && is_lm ? j + 1 : 0];
-  const T type_lm = (T)(wc.eflag[has && is_lm ? j + 1 : 0] >> 1);
+  unsigned char* const wbase = wsm + (size_t)warp * lay.warp;
+  Ent* const ent = (Ent*)(wbase + lay.ent) + grp * E;    // my env's entity table
 
-  // ---- state: all N agents in every lane, one landmark per lane ---------------------------------
-  T px[N], py[N], vx[N], vy[N];
+  // ---- lane constants: my "other" is an agent in every chunk (j < N-1) or landmark j+1-N in every
+  //      chunk, and the agents are alike, so its size / type / flags do not depend on the chunk ----------
+  const int e_hi = has ? j + 1 : 0;                      // the other in chunks i <= j (i > j: e_hi - 1)
+  const int fl_o = wc.eflag[e_hi];
+  const T size_o = wc.size[e_hi], type_o = (T)(fl_o >> 1);
+  const bool cpair = has && (wc.eflag[0] & 1) && (fl_o & 1);
+  const bool colc = has && (e_hi < N || (p.cost_obstacles && (fl_o >> 1) == GSM_ENT_OBSTACLE));
+  const int goal_i = (has && p.own_goal_always) ? j - (N - 1) : -1;   // chunk in which my landmark is the agent's own goal
+
+  // ---- state: my own agent in registers, everything in the entity table ---------------------------
+  T mx, my, mvx, mvy;
   {
-    const T* a = p.agent_state + (int64_t)env * N * 4;
-#pragma unroll
-    for (int i = 0; i < N; i++) { px[i] = a[4 * i]; py[i] = a[4 * i + 1]; vx[i] = a[4 * i + 2]; vy[i] = a[4 * i + 3]; }
+    const T* a = p.agent_state + ((int64_t)env * N + ja) * 4;
+    mx = a[0]; my = a[1]; mvx = a[2]; mvy = a[3];
   }
-  T lmx = 0, lmy = 0;
-  if (is_lm && has) {
+  if (own) { Ent s; s.x = mx; s.y = my; s.vx = mvx; s.vy = mvy; ent[j] = s; }
+  if (has && j + 1 >= N) {                               // lane j also holds landmark j + 1 - N
     const T* l = p.lm_pos + ((int64_t)env * L + (j + 1 - N)) * 2;
-    lmx = l[0]; lmy = l[1];
+    Ent s; s.x = l[0]; s.y = l[1]; s.vx = 0; s.vy = 0; ent[j + 1] = s;
   }
   int t_now = p.t[env];
   const bool auto_reset = MODE == 2 && p.auto_reset != 0;
   int ep = auto_reset ? p.episode[env] : 0;
   const int ep0 = ep;
+  const T accel_m = wc.accel[ja], mass_m = wc.mass[ja], massinv_m = wc.mass_inv[ja], maxsp_m = wc.maxsp[ja];
 
-  // butterfly all-reduce over the env's GW lanes; IEEE addition commutes, so every lane of the
-  // group ends with the same bits and the redundant integrations stay identical
-  auto reduce = [&](T (&fx)[N], T (&fy)[N]) {
-#pragma unroll
-    for (int m = GW / 2; m >= 1; m >>= 1) {
-#pragma unroll
-      for (int i = 0; i < N; i++) { fx[i] = fx[i] + shfl_xor(fx[i], m); fy[i] = fy[i] + shfl_xor(fy[i], m); }
-    }
-  };
-
-  // ---- warp-uniform slot bases, 32-bit lane offsets ----------------------------------------------
+  // ---- slot bases (warp-uniform), offsets of this warp / this lane ------------------------------------
   const unsigned char* b_act = (const unsigned char*)p.actions;
   unsigned char* b_obs = (unsigned char*)p.obs;
   unsigned char* b_idx = (unsigned char*)p.nbr_idx;
   unsigned char* b_feat = (unsigned char*)p.nbr_feat;
-  unsigned char* b_cnt = (unsigned char*)p.nbr_cnt;
-  unsigned char* b_adj = (unsigned char*)p.adj;
-  unsigned char* b_rew = (unsigned char*)p.reward;
-  unsigned char* b_cost = (unsigned char*)p.cost;
   unsigned char* b_done = (unsigned char*)p.done;
-  unsigned char* b_asg = (unsigned char*)p.assign;
-  const unsigned row0 = (unsigned)env * N;              // first agent row of my env
-  const int ja = j % N, jp = j / N;                     // roles behind the chunk loop: agent, part
-  // staging: [feat EPW*N*K rows][idx EPW*N*K][obs EPW*N rows], two buffers per warp
-  const unsigned sz_feat = (unsigned)(EPW * N * K * GSM_NBR_FEAT_DIM * sizeof(T)), sz_idx = (unsigned)(EPW * N * K * 4),
-                 sz_obs = (unsigned)(EPW * N * GSM_OBS_DIM * sizeof(T)), sz_buf = sz_feat + sz_idx + sz_obs;
-  unsigned char* const stage0 = wsm + (size_t)warp * 2 * sz_buf;
-  const unsigned lrow0 = (unsigned)grp * N * K;         // my env's first neighbour row inside the warp's block
-  const unsigned w_feat = (unsigned)env_w0 * (unsigned)(N * K * GSM_NBR_FEAT_DIM * sizeof(T)),   // warp offsets in a slot
-                 w_idx = (unsigned)env_w0 * (unsigned)(N * K * 4),
-                 w_obs = (unsigned)env_w0 * (unsigned)(N * GSM_OBS_DIM * sizeof(T));
+  const unsigned wrow0 = (unsigned)env_w0 * N;          // first agent row of the warp
+  // the five per-agent scalar blocks leave as 16-byte pieces, staged contiguously in piece order
+  // (cnt, adj, cost, reward, assign): lane q owns piece q
+  unsigned char* c_role = nullptr;                       // my piece in global memory (advanced by its array's stride)
+  int64_t role_stride = ss.nbr_cnt;                      // fp32: one stride for all five (launcher-checked)
+  {
+    const int q = lane;
+    if (q < PC4) c_role = (unsigned char*)p.nbr_cnt + wrow0 * 4u + q * 16;
+    else if (q < 2 * PC4) { c_role = (unsigned char*)p.adj + wrow0 * 4u + (q - PC4) * 16; if (RB != 4) role_stride = ss.adj; }
+    else if (q < 2 * PC4 + PCT) { c_role = (unsigned char*)p.cost + wrow0 * (unsigned)RB + (q - 2 * PC4) * 16; if (RB != 4) role_stride = ss.cost; }
+    else if (q < 2 * PC4 + 2 * PCT) { c_role = (unsigned char*)p.reward + wrow0 * (unsigned)RB + (q - 2 * PC4 - PCT) * 16; if (RB != 4) role_stride = ss.reward; }
+    else if (q < NPIECE) { c_role = (unsigned char*)p.assign + wrow0 * 4u + (q - 2 * PC4 - 2 * PCT) * 16; if (RB != 4) role_stride = ss.assign; }
+  }
+  const bool role_on = lane < NPIECE && (!OBS || lane < 2 * PC4 || lane >= 2 * PC4 + 2 * PCT);
+  // assign[i] = i never changes: both staging buffers get it once
+  if (own) {
+    *(int32_t*)(wbase + lay.asg + (grp * N + j) * 4) = j;
+    *(int32_t*)(wbase + lay.buf + lay.asg + (grp * N + j) * 4) = j;
+  }
 
-  // action of agent j on lane j < N, prefetched one step ahead; that lane also turns it into the
-  // control force accel[j] * u so that the N agents' forces cost one lookup per lane, not N
+  // action of my own agent, prefetched one step ahead
   const bool discrete = p.action_mode == GSM_ACT_DISCRETE;
-  const unsigned act_off = discrete ? (row0 + (j < N ? j : 0)) * 4u : (row0 + (j < N ? j : 0)) * 2u * (unsigned)sizeof(T);
-  const T accel_m = wc.accel[j < N ? j : 0];
+  const unsigned act_off = discrete ? ((unsigned)env * N + ja) * 4u : ((unsigned)env * N + ja) * 2u * (unsigned)RB;
   int act_next = 0;
   T actx_next = 0, acty_next = 0;
   if (!OBS) {
     if (discrete) act_next = *(const int32_t*)(b_act + act_off);
     else { actx_next = ((const T*)(b_act + act_off))[0]; acty_next = ((const T*)(b_act + act_off))[1]; }
   }
+  __syncwarp();
 
-  T fcx[N], fcy[N];                                      // contact force on agent i for the NEXT integration
-#pragma unroll
-  for (int i = 0; i < N; i++) { fcx[i] = 0; fcy[i] = 0; }
+  T fox = 0, foy = 0;                                    // contact force on my own agent for the NEXT integration
   // `pro` (warp-uniform): a prologue pass — geometry and contact forces of the CURRENT positions only,
   // no integration, no outputs, no step consumed.  The first pass of a launch and the pass after an
   // in-kernel re-draw are prologues; every other pass is one env step.  One copy of the code serves both.
@@ -181,83 +203,80 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   int step = 0;
   while (step < n_steps) {
     if (!OBS && !pro) {
-      // ---- SPEC §2 + §4 for all N agents, redundantly on every lane ---------------------------------
+      // ---- SPEC §2 + §4 for my own agent (lanes j >= N shadow agent 0 and publish nothing) -----------
       T ux = actx_next, uy = acty_next;
       if (discrete) {
         const int a = act_next;
         ux = 0; uy = 0;
         if (a >= 0 && a < p.n_actions) { ux = p.discrete_u[a][0]; uy = p.discrete_u[a][1]; }
       }
-      const T cfx = accel_m * ux, cfy = accel_m * uy;
       if (step + 1 < n_steps) b_act += ss.actions;      // the last step re-reads its own, valid, address
       if (discrete) act_next = *(const int32_t*)(b_act + act_off);
       else { actx_next = ((const T*)(b_act + act_off))[0]; acty_next = ((const T*)(b_act + act_off))[1]; }
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        const T fx = shfl(FULL, cfx, shift + i) + fcx[i], fy = shfl(FULL, cfy, shift + i) + fcy[i];
-        T nvx = vx[i] * p.one_minus_damp, nvy = vy[i] * p.one_minus_damp;
-        nvx = nvx + A::div_const(fx, wc.mass[i], wc.mass_inv[i]) * p.dt;
-        nvy = nvy + A::div_const(fy, wc.mass[i], wc.mass_inv[i]) * p.dt;
-        if (wc.maxsp[i] > (T)0) {
-          const T sp = A::sqrt(nvx * nvx + nvy * nvy);
-          if (sp > wc.maxsp[i]) { nvx = A::div(nvx, sp) * wc.maxsp[i]; nvy = A::div(nvy, sp) * wc.maxsp[i]; }
-        }
-        vx[i] = nvx; vy[i] = nvy;
-        px[i] = px[i] + nvx * p.dt; py[i] = py[i] + nvy * p.dt;
+      const T fx = accel_m * ux + fox, fy = accel_m * uy + foy;
+      T nvx = mvx * p.one_minus_damp, nvy = mvy * p.one_minus_damp;
+      nvx = nvx + A::div_const(fx, mass_m, massinv_m) * p.dt;
+      nvy = nvy + A::div_const(fy, mass_m, massinv_m) * p.dt;
+      if (maxsp_m > (T)0) {
+        const T sp = A::sqrt(nvx * nvx + nvy * nvy);
+        if (sp > maxsp_m) { nvx = A::div(nvx, sp) * maxsp_m; nvy = A::div(nvy, sp) * maxsp_m; }
       }
+      mvx = nvx; mvy = nvy;
+      mx = mx + nvx * p.dt; my = my + nvy * p.dt;
       t_now += 1;
+      if (own) { Ent s; s.x = mx; s.y = my; s.vx = mvx; s.vy = mvy; ent[j] = s; }
+      __syncwarp();
     }
     const bool st_on = !pro;                             // warp-uniform: this pass produces outputs
-    unsigned char* const sb = stage0 + (step & 1) * sz_buf;
-    // the bulk copies that read this buffer two steps ago must have finished reading it; the first
+    unsigned char* const sb = wbase + (step & 1) * lay.buf;
+    // the bulk copy that read this buffer two steps ago must have finished reading it; the first
     // ballot below orders every lane's STS behind lane 0's wait
     if (st_on && bulk && lane == 0) bulk_wait_read<1>();
 
     // ---- SPEC §6-7: one chunk per agent; the pair's row is known after the chunk's own ballot -----
-    T gxs = 0, gys = 0, rs = 0;                          // lanes N-1 .. 2N-2: goal vector / reward of agent j-(N-1)
-    int cnt_m = 0, ncol_m = 0;                           // lane roles behind the loop: values of agent ja
-    unsigned adj_m = 0;
+    T fcx[N], fcy[N];
+    T gxs = 0, gys = 0, gd = 0;                          // lane N-1+i: goal vector / distance of agent i
     bool anyc = false;
 #pragma unroll
     for (int i = 0; i < N; i++) {
-      // the other entity of chunk i: an agent out of my own registers (lanes j < N-1) or my landmark
-      T ex = lmx, ey = lmy, evx = 0, evy = 0, size_o = size_lm, type_o = type_lm;
-#pragma unroll
-      for (int a = 0; a < N - 1; a++) {
-        const int oa = a + (a >= i ? 1 : 0);
-        if (j == a) { ex = px[oa]; ey = py[oa]; evx = vx[oa]; evy = vy[oa]; size_o = wc.size[oa]; type_o = (T)(wc.eflag[oa] >> 1); }
-      }
-      const int e = j + (j >= i ? 1 : 0);
-      const T dmin = wc.size[i] + size_o;
-      const T dx = ex - px[i], dy = ey - py[i];
+      const int e = e_hi - (j < i ? 1 : 0);
+      const Ent si = ent[i], so = ent[e];
+      const T dx = so.x - si.x, dy = so.y - si.y;
       const T dist = A::sqrt(dx * dx + dy * dy);
-      const bool nb = (has && dist < p.Rs) || ((cfl >> (16 + i)) & 1u);
-      const bool col = ((cfl >> (8 + i)) & 1u) && dist < dmin;
+      const T dmin = wc.size[i] + size_o;
+      const bool nb = (has && dist < p.Rs) || goal_i == i;
+      const bool col = colc && dist < dmin;
       const unsigned bits = (__ballot_sync(FULL, nb) >> shift) & low_mask(GW);
       const unsigned cbits = (__ballot_sync(FULL, col) >> shift) & low_mask(GW);
       int cnt = __popc(bits);
-      const int rank = __popc(bits & below);
+      const int rank = __popc(bits & low_mask(j));
       const int pos = nb ? rank : cnt + (j - rank);
       if (has && pos < K && st_on) {
-        const unsigned lr = lrow0 + (unsigned)(i * K + pos);
-        *(int32_t*)(sb + sz_feat + lr * 4u) = nb ? e : -1;
-        T* f = (T*)(sb + lr * (unsigned)(GSM_NBR_FEAT_DIM * sizeof(T)));
+        const unsigned lr = (unsigned)((grp * N + i) * K + pos);
+        *(int32_t*)(sb + lay.idx + lr * 4u) = nb ? e : -1;
+        T* f = (T*)(sb + lr * (unsigned)(GSM_NBR_FEAT_DIM * RB));
         const T z = (T)0;
-        st2<T>(f, nb ? dx : z, nb ? dy : z);
-        st2<T>(f + 2, nb ? evx - vx[i] : z, nb ? evy - vy[i] : z);
-        st2<T>(f + 4, nb ? dist : z, nb ? type_o : z);
+        if (nb) { st2<T>(f, dx, dy); st2<T>(f + 2, so.vx - si.vx, so.vy - si.vy); st2<T>(f + 4, dist, type_o); }
+        else { st2<T>(f, z, z); st2<T>(f + 2, z, z); st2<T>(f + 4, z, z); }
       }
       if (cnt > K) cnt = K;
-      // entity-indexed adjacency: open a zero bit at the agent's own index i
-      const unsigned ebits = (bits & low_mask(i)) | ((bits & ~low_mask(i)) << 1);
-      if (ja == i) { cnt_m = cnt; adj_m = ebits; ncol_m = __popc(cbits); }
-      if (j == N - 1 + i) {                               // my landmark is this agent's goal
-        gxs = dx; gys = dy;
-        rs = ((T)0 - p.w_dist * dist) + (dist < p.goal_tol ? p.w_goal : (T)0);
+      if (st_on && j < 3) {                               // lanes 0, 1, 2 stage cnt, adj, cost of agent i
+        // entity-indexed adjacency: open a zero bit at the agent's own index i
+        const unsigned ebits = (bits & low_mask(i)) | ((bits & ~low_mask(i)) << 1);
+        const unsigned ao = (unsigned)(grp * N + i);
+        if (RB == 4) {                                    // three equal 4-byte blocks in a row: one store
+          const unsigned v = j == 0 ? (unsigned)cnt : (j == 1 ? ebits : __float_as_uint((float)__popc(cbits)));
+          if (!OBS || j < 2) *(uint32_t*)(sb + lay.cnt + (unsigned)j * RS4 + ao * 4u) = v;
+        } else {
+          if (j == 0) *(int32_t*)(sb + lay.cnt + ao * 4u) = cnt;
+          else if (j == 1) *(uint32_t*)(sb + lay.adj + ao * 4u) = ebits;
+          else if (!OBS) *(T*)(sb + lay.cost + ao * (unsigned)RB) = (T)__popc(cbits);
+        }
       }
+      if (j == N - 1 + i) { gxs = dx; gys = dy; gd = dist; }   // my landmark is this agent's goal
       if (!OBS) {                                         // SPEC §3 for the next step, on the same geometry:
         fcx[i] = 0; fcy[i] = 0;                           // the force uses p_i - p_e = -d, exactly
-        if ((cfl >> i) & 1u) {
+        if (cpair) {
           const T x = A::div_const(-(dist - dmin), p.km, p.km_inv);
           if (!(Prec<T>::kCut && x < (T)(-kFarCut))) {
             const T pen = softplus1(x) * p.km;
@@ -268,63 +287,75 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         }
       }
     }
-    // all-zero partial forces sum to exactly zero: the butterfly is skipped when no lane of the warp has a term
-    if (!OBS && (pro || step + 1 < n_steps) && __any_sync(FULL, anyc)) reduce(fcx, fcy);
+    // Contact forces: butterfly all-reduce over the env's GW lanes (IEEE addition commutes: every lane of
+    // the group ends with the same bits), each owner keeps its agent's sum.  All-zero partials sum to
+    // exactly zero, so the butterfly is skipped when no lane of the warp has a term.
+    if (!OBS && (pro || step + 1 < n_steps)) {
+      fox = 0; foy = 0;
+      if (__any_sync(FULL, anyc)) {
+#pragma unroll
+        for (int m = GW / 2; m >= 1; m >>= 1) {
+#pragma unroll
+          for (int i = 0; i < N; i++) { fcx[i] = fcx[i] + shfl_xor(fcx[i], m); fcy[i] = fcy[i] + shfl_xor(fcy[i], m); }
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) if (ja == i) { fox = fcx[i]; foy = fcy[i]; }
+      }
+    }
 
     if (st_on) {
-      // ---- per-agent outputs by lane roles ---------------------------------------------------------
+      // ---- per-agent outputs --------------------------------------------------------------------------
+      T* const sobs = (T*)(sb + lay.obs) + (unsigned)grp * (N * GSM_OBS_DIM);
+      if (own) { st2<T>(sobs + j * GSM_OBS_DIM, mvx, mvy); st2<T>(sobs + j * GSM_OBS_DIM + 2, mx, my); }
+      T rs = ((T)0 - p.w_dist * gd) + (gd < p.goal_tol ? p.w_goal : (T)0);
       if (p.share_reward && !OBS) {
         T s = shfl(FULL, rs, shift + N - 1);
 #pragma unroll
         for (int k = 1; k < N; k++) s = s + shfl(FULL, rs, shift + N - 1 + k);
         rs = s / (T)N;
       }
-      // obs: lanes 0..N-1 stage (vx, vy) of agent j, lanes N..2N-1 (px, py) of agent j-N, lanes N-1..2N-2 the goal part
-      T* const so = (T*)(sb + sz_feat + sz_idx) + (unsigned)grp * (N * GSM_OBS_DIM);
-      if (j < 2 * N) {
-        T a0 = 0, a1 = 0;
-#pragma unroll
-        for (int k = 0; k < N; k++)
-          if (ja == k) { a0 = jp == 0 ? vx[k] : px[k]; a1 = jp == 0 ? vy[k] : py[k]; }
-        st2<T>(so + ja * GSM_OBS_DIM + 2 * jp, a0, a1);
-      }
       if (j >= N - 1 && j < 2 * N - 1) {
-        st2<T>(so + (j - (N - 1)) * GSM_OBS_DIM + 4, gxs, gys);
-        if (!OBS && active) *(T*)(b_rew + (row0 + (j - (N - 1))) * (unsigned)sizeof(T)) = rs;
+        const unsigned ao = (unsigned)(j - (N - 1));
+        st2<T>(sobs + ao * GSM_OBS_DIM + 4, gxs, gys);
+        if (!OBS) *(T*)(sb + lay.rew + ((unsigned)grp * N + ao) * (unsigned)RB) = rs;
       }
-      // lanes 0..N-1: cnt, cost, done of agent j; lanes N..2N-1: adj, assign of agent j-N
-      if (j < 2 * N && active) {
-        const unsigned r = row0 + ja;
-        if (jp == 0) {
-          *(int32_t*)(b_cnt + r * 4u) = cnt_m;
-          if (!OBS) {
-            *(T*)(b_cost + r * (unsigned)sizeof(T)) = (T)ncol_m;
-            b_done[r] = (uint8_t)(t_now >= p.episode_length);
-          }
-        } else {
-          *(uint32_t*)(b_adj + r * 4u) = adj_m;
-          *(int32_t*)(b_asg + r * 4u) = ja;
-        }
-      }
-      // ---- the staged rows leave: three bulk copies, or (ragged / masked / unaligned warps) plain stores ----
+      if (!OBS && own && active) b_done[(unsigned)env * N + j] = (uint8_t)(t_now >= p.episode_length);
+      // ---- the staged blocks leave -----------------------------------------------------------------------
       if (bulk) {
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          bulk_store(b_feat + w_feat, sb, sz_feat);
-          bulk_store(b_idx + w_idx, sb + sz_feat, sz_idx);
-          bulk_store(b_obs + w_obs, sb + sz_feat + sz_idx, sz_obs);
+          bulk_store(b_feat + wrow0 * (unsigned)(K * GSM_NBR_FEAT_DIM * RB), sb, lay.idx);
           bulk_commit();
         }
+        const unsigned n_idx = (lay.obs - lay.idx) / 16, n_obs = (lay.cnt - lay.obs) / 16;
+        V* const g_idx = (V*)(b_idx + wrow0 * (unsigned)(K * 4));
+        V* const g_obs = (V*)(b_obs + wrow0 * (unsigned)(GSM_OBS_DIM * RB));
+        const V* const s_idx = (const V*)(sb + lay.idx);
+        const V* const s_obs = (const V*)(sb + lay.obs);
+        if (lane < n_idx) g_idx[lane] = s_idx[lane];
+        if (lane + 32 < n_idx) g_idx[lane + 32] = s_idx[lane + 32];
+        if (lane < n_obs) g_obs[lane] = s_obs[lane];
+        if (lane + 32 < n_obs) g_obs[lane + 32] = s_obs[lane + 32];
+        if (role_on) *(V*)c_role = *(const V*)(sb + lay.cnt + lane * 16);
       } else {
+        // ragged / masked / unaligned warps: word-wise, per-env predicated
         __syncwarp();
-        const unsigned wf = sz_feat / (4 * EPW), wi = sz_idx / (4 * EPW), wo = sz_obs / (4 * EPW);   // words per env
-        for (unsigned q = lane; q < sz_feat / 4; q += 32)
-          if ((act_bits >> ((q / wf) * GW)) & 1u) ((uint32_t*)(b_feat + w_feat))[q] = ((const uint32_t*)sb)[q];
-        for (unsigned q = lane; q < sz_idx / 4; q += 32)
-          if ((act_bits >> ((q / wi) * GW)) & 1u) ((uint32_t*)(b_idx + w_idx))[q] = ((const uint32_t*)(sb + sz_feat))[q];
-        for (unsigned q = lane; q < sz_obs / 4; q += 32)
-          if ((act_bits >> ((q / wo) * GW)) & 1u) ((uint32_t*)(b_obs + w_obs))[q] = ((const uint32_t*)(sb + sz_feat + sz_idx))[q];
+        auto copy_words = [&](unsigned char* g, unsigned soff, unsigned bytes) {
+          const unsigned wpe = bytes / (4 * EPW);         // words per env
+          for (unsigned q = lane; q < bytes / 4; q += 32)
+            if ((act_bits >> ((q / wpe) * GW)) & 1u) ((uint32_t*)g)[q] = ((const uint32_t*)(sb + soff))[q];
+        };
+        copy_words(b_feat + wrow0 * (unsigned)(K * GSM_NBR_FEAT_DIM * RB), lay.feat, lay.idx - lay.feat);
+        copy_words(b_idx + wrow0 * (unsigned)(K * 4), lay.idx, lay.obs - lay.idx);
+        copy_words(b_obs + wrow0 * (unsigned)(GSM_OBS_DIM * RB), lay.obs, lay.cnt - lay.obs);
+        copy_words((unsigned char*)p.nbr_cnt + (int64_t)step * ss.nbr_cnt + wrow0 * 4u, lay.cnt, RS4);
+        copy_words((unsigned char*)p.adj + (int64_t)step * ss.adj + wrow0 * 4u, lay.adj, RS4);
+        copy_words((unsigned char*)p.assign + (int64_t)step * ss.assign + wrow0 * 4u, lay.asg, RS4);
+        if (!OBS) {
+          copy_words((unsigned char*)p.reward + (int64_t)step * ss.reward + wrow0 * (unsigned)RB, lay.rew, RST);
+          copy_words((unsigned char*)p.cost + (int64_t)step * ss.cost + wrow0 * (unsigned)RB, lay.cost, RST);
+        }
         __syncwarp();
       }
     }
@@ -335,38 +366,43 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     if (MODE == 2 && auto_reset) {
       const bool fin = t_now >= p.episode_length;
       if (__any_sync(FULL, fin)) {
+        __syncwarp();                                     // every lane has read the old table
         if (fin) {
           const uint64_t genv = (uint64_t)(p.env_offset + env);
-#pragma unroll
-          for (int i = 0; i < N; i++) {
-            spawn_draw<T>(genv, ep, i, p.seed, p.ext[GSM_ENT_AGENT], px[i], py[i]);
-            vx[i] = 0; vy[i] = 0;
+          spawn_draw<T>(genv, ep, ja, p.seed, p.ext[GSM_ENT_AGENT], mx, my);
+          mvx = 0; mvy = 0;
+          if (own) { Ent s; s.x = mx; s.y = my; s.vx = 0; s.vy = 0; ent[j] = s; }
+          if (has && j + 1 >= N) {
+            Ent s; s.vx = 0; s.vy = 0;
+            spawn_draw<T>(genv, ep, j + 1, p.seed, p.ext[wc.eflag[j + 1] >> 1], s.x, s.y);
+            ent[j + 1] = s;
           }
-          if (is_lm && has) spawn_draw<T>(genv, ep, j + 1, p.seed, p.ext[wc.eflag[j + 1] >> 1], lmx, lmy);
           t_now = 0;
           ep += 1;
         }
+        __syncwarp();
         pro = step + 1 < n_steps;                         // the new positions need their forces
       }
     }
-    b_obs += ss.obs; b_idx += ss.nbr_idx; b_feat += ss.nbr_feat; b_cnt += ss.nbr_cnt; b_adj += ss.adj;
-    b_rew += ss.reward; b_cost += ss.cost; b_done += ss.done; b_asg += ss.assign;
+    b_obs += ss.obs; b_idx += ss.nbr_idx; b_feat += ss.nbr_feat; b_done += ss.done;
+    c_role += role_stride;
     step++;
   }
-  if (bulk && lane == 0) bulk_wait_read<0>();            // shared memory must outlive the copies that read it
+  if (bulk && lane == 0) bulk_wait_read<0>();            // shared memory must outlive the copy that reads it
 
   // ---- state back to HBM ------------------------------------------------------------------------------
   if (!OBS && active) {
+    if (own) {
+      T* a = p.agent_state + ((int64_t)env * N + j) * 4;
+      st2<T>(a, mx, my); st2<T>(a + 2, mvx, mvy);
+    }
     if (j == 0) {
-      T* a = p.agent_state + (int64_t)env * N * 4;
-#pragma unroll
-      for (int i = 0; i < N; i++) { st2<T>(a + 4 * i, px[i], py[i]); st2<T>(a + 4 * i + 2, vx[i], vy[i]); }
       p.t[env] = t_now;
       if (auto_reset && ep != ep0) p.episode[env] = ep;
     }
-    if (auto_reset && ep != ep0 && is_lm && has) {
+    if (auto_reset && ep != ep0 && has && j + 1 >= N) {
       T* l = p.lm_pos + ((int64_t)env * L + (j + 1 - N)) * 2;
-      l[0] = lmx; l[1] = lmy;
+      l[0] = ent[j + 1].x; l[1] = ent[j + 1].y;
     }
   }
 }

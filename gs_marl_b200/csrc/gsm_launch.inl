@@ -186,6 +186,8 @@ static int launch_spec_one(const KParams<GSM_REAL>& kp, int n_steps, const StepS
 static bool has_wide(const HostParams& hp) {
   if (!spec_enabled() || env_int("GSM_NO_WIDE", 0) != 0 || env_int("GSM_SPEC_P", 0) != 0) return false;
   if (hp.scenario != GSM_SCN_NAVIGATION || !hp.h_consts) return false;
+  for (int i = 1; i < hp.N; i++)          // the agents must be alike (size, collide): chunk-independent lane constants
+    if (hp.h_size[i] != hp.h_size[0] || (hp.h_eflag[i] & 1) != (hp.h_eflag[0] & 1)) return false;
   // 32-bit lane offsets into one slot of the largest output
   if (hp.n_envs * hp.N * hp.K * (int64_t)(GSM_NBR_FEAT_DIM * sizeof(GSM_REAL)) >= (1ll << 31)) return false;
 #define X(n, l) if (hp.N == n && hp.L == l) return true;
@@ -206,7 +208,7 @@ static int launch_wide_one(const HostParams& hp, const KParams<GSM_REAL>& kp, in
     wc.accel[i] = (T)hp.h_accel[i]; wc.maxsp[i] = (T)hp.h_maxsp[i];
   }
   const int64_t grid = (kp.n_envs + EPW * WPC - 1) / (EPW * WPC);
-  const size_t smem = wide_smem_bytes((int)sizeof(T), N, kp.K, EPW);
+  const size_t smem = wide_smem_bytes((int)sizeof(T), N, E, kp.K, EPW);
   auto k = observe ? env_wide_kernel<T, N, L, 1> : (kp.auto_reset ? env_wide_kernel<T, N, L, 2> : env_wide_kernel<T, N, L, 0>);
   static bool attr_done[3] = {false, false, false};      // per instance (this function is one per (T, N, L))
   const int which = observe ? 1 : (kp.auto_reset ? 2 : 0);
@@ -232,7 +234,9 @@ int GSM_SFX(launch_spec)(const HostParams& hp, const gsm_step_io& io, int n_step
   ss.actions = rs.actions; ss.obs = rs.obs; ss.nbr_idx = rs.nbr_idx; ss.nbr_feat = rs.nbr_feat;
   ss.nbr_cnt = rs.nbr_cnt; ss.adj = rs.adj; ss.reward = rs.reward; ss.cost = rs.cost;
   ss.done = rs.done; ss.assign = rs.assign;
-  if (has_wide(hp)) {
+  const bool one_stride = sizeof(GSM_REAL) != 4 || (ss.nbr_cnt == ss.adj && ss.adj == ss.reward && ss.reward == ss.cost &&
+                                                    ss.cost == ss.assign);
+  if (has_wide(hp) && one_stride) {
 #define X(n, l) if (hp.N == n && hp.L == l) return launch_wide_one<n, l>(hp, kp, n_steps, ss, observe != 0, st);
     GSM_WIDE_TABLE(X)
 #undef X
