@@ -48,6 +48,37 @@ template <typename T> struct WideMinBlocks { static constexpr int value = sizeof
 __device__ __forceinline__ float softplus1(float x) { return fmaxf(x, 0.f) + r_log1p(r_exp(-fabsf(x))); }
 __device__ __forceinline__ double softplus1(double x) { return fmax(x, 0.0) + r_log1p(r_exp(-fabs(x))); }
 
+// Loop-invariant lane constants: ptxas prefers to REBUILD them inside the step loop (S2R, integer
+// divisions, indexed constant loads: ~150 instructions per warp-step measured) over holding a register.
+// A value that went through a shuffle cannot be rematerialised; it costs one SHFL per launch.
+__device__ __forceinline__ int keep(int v) { return __shfl_sync(0xffffffffu, v, threadIdx.x & 31); }
+__device__ __forceinline__ unsigned keep(unsigned v) { return __shfl_sync(0xffffffffu, v, threadIdx.x & 31); }
+__device__ __forceinline__ float keep(float v) { return __shfl_sync(0xffffffffu, v, threadIdx.x & 31); }
+__device__ __forceinline__ double keep(double v) { return __shfl_sync(0xffffffffu, v, threadIdx.x & 31); }
+
+// Shared-memory access through 32-bit shared-space addresses held in (kept) registers: a generic pointer
+// into the dynamic array makes ptxas rebuild the shared window base (S2UR + UMOV + ULEA) at every use.
+__device__ __forceinline__ void sts(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts(unsigned a, int v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts2(unsigned a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(a), "f"(x), "f"(y) : "memory"); }
+__device__ __forceinline__ void sts2(unsigned a, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(a), "d"(x), "d"(y) : "memory"); }
+__device__ __forceinline__ void sts4(unsigned a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts4(unsigned a, double x, double y, double z, double w) { sts2(a, x, y); sts2(a + 16, z, w); }
+__device__ __forceinline__ void lds4(unsigned a, float& x, float& y, float& z, float& w) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void lds4(unsigned a, double& x, double& y, double& z, double& w) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a) : "memory");
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(z), "=d"(w) : "r"(a + 16) : "memory");
+}
+__device__ __forceinline__ float4 lds16(unsigned a) {
+  float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory"); return v;
+}
+
 template <typename T>
 __device__ __forceinline__ T shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
@@ -95,7 +126,8 @@ template <typename T, int N, int L, int MODE>
 __global__ void __launch_bounds__(kWideThreads, WideMinBlocks<T>::value)
 env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
                 const __grid_constant__ StepStrides ss,
-                const __grid_constant__ WideConsts<T, N, N + L> wc) {
+                const __grid_constant__ WideConsts<T, N, N + L> wc,
+                const __grid_constant__ WideSmem lay) {
   constexpr int E = N + L, M = E - 1, GW = wide_pow2(M), EPW = 32 / GW;
   constexpr bool OBS = MODE == 1;
   constexpr unsigned FULL = 0xffffffffu;
@@ -111,9 +143,9 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   typedef float4 V;                                        // a 16-byte piece
   extern __shared__ __align__(128) unsigned char wsm[];
   const int K = p.K;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = keep((int)(threadIdx.x & 31)), warp = threadIdx.x >> 5;
   const int grp = lane / GW, j = lane % GW, shift = grp * GW;
-  const int env_w0 = (int)(((int64_t)blockIdx.x * (kWideThreads / 32) + warp) * EPW);
+  const int env_w0 = keep((int)(((int64_t)blockIdx.x * (kWideThreads / 32) + warp) * EPW));
   bool active = env_w0 + grp < p.n_envs;
   if (OBS && p.mask != nullptr && active) active = p.mask[(int64_t)(env_w0 + grp) * p.mask_stride] != 0;
   const int env = active ? env_w0 + grp : 0;            // idle groups shadow env 0, never store
@@ -121,7 +153,6 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   const bool own = j < N;                               // I own (integrate, publish) agent j
   const int ja = own ? j : 0;
   const unsigned act_bits = __ballot_sync(FULL, active);
-  const WideSmem lay = wide_smem_layout(RB, N, E, K, EPW);
   // staged bulk path: the warp's EPW envs all exist (and are unmasked) and every slot is 16-byte aligned
   const bool bulk = act_bits == FULL &&
       ((((uintptr_t)p.obs | (uintptr_t)p.nbr_idx | (uintptr_t)p.nbr_feat | (uintptr_t)p.nbr_cnt | (uintptr_t)p.adj |
@@ -129,17 +160,21 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
          (uintptr_t)ss.nbr_feat | (uintptr_t)ss.nbr_cnt | (uintptr_t)ss.adj | (uintptr_t)ss.assign |
          (uintptr_t)ss.reward | (uintptr_t)ss.cost) & 15) == 0);
 
-  unsigned char* const wbase = wsm + (size_t)warp * lay.warp;
-  Ent* const ent = (Ent*)(wbase + lay.ent) + grp * E;    // my env's entity table
+  constexpr unsigned ES = (unsigned)sizeof(Ent);
+  const unsigned sa_w = keep(smem_u32(wsm) + (unsigned)warp * lay.warp);                 // my warp's block (shared-space address)
+  const unsigned sa_ent = keep(smem_u32(wsm) + (unsigned)warp * lay.warp + lay.ent + (unsigned)(grp * E) * ES);   // my env's entity table
 
   // ---- lane constants: my "other" is an agent in every chunk (j < N-1) or landmark j+1-N in every
   //      chunk, and the agents are alike, so its size / type / flags do not depend on the chunk ----------
   const int e_hi = has ? j + 1 : 0;                      // the other in chunks i <= j (i > j: e_hi - 1)
   const int fl_o = wc.eflag[e_hi];
-  const T size_o = wc.size[e_hi], type_o = (T)(fl_o >> 1);
-  const bool cpair = has && (wc.eflag[0] & 1) && (fl_o & 1);
-  const bool colc = has && (e_hi < N || (p.cost_obstacles && (fl_o >> 1) == GSM_ENT_OBSTACLE));
-  const int goal_i = (has && p.own_goal_always) ? j - (N - 1) : -1;   // chunk in which my landmark is the agent's own goal
+  const T size_o = keep(wc.size[e_hi]), type_o = keep((T)(fl_o >> 1));
+  // bit 0: contact pair, bit 1: counts as a collision, bits 8..: chunk in which my landmark is the agent's own goal (+1)
+  const unsigned lfl = keep((unsigned)((has && (wc.eflag[0] & 1) && (fl_o & 1)) ? 1u : 0u) |
+                            ((has && (e_hi < N || (p.cost_obstacles && (fl_o >> 1) == GSM_ENT_OBSTACLE))) ? 2u : 0u) |
+                            (((has && p.own_goal_always && j >= N - 1 && j < 2 * N - 1) ? (unsigned)(j - (N - 1) + 1) : 0u) << 8));
+  const bool cpair = lfl & 1u, colc = lfl & 2u;
+  const int goal_i = (int)(lfl >> 8) - 1;
 
   // ---- state: my own agent in registers, everything in the entity table ---------------------------
   T mx, my, mvx, mvy;
@@ -147,16 +182,16 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     const T* a = p.agent_state + ((int64_t)env * N + ja) * 4;
     mx = a[0]; my = a[1]; mvx = a[2]; mvy = a[3];
   }
-  if (own) { Ent s; s.x = mx; s.y = my; s.vx = mvx; s.vy = mvy; ent[j] = s; }
+  if (own) sts4(sa_ent + (unsigned)j * ES, mx, my, mvx, mvy);
   if (has && j + 1 >= N) {                               // lane j also holds landmark j + 1 - N
     const T* l = p.lm_pos + ((int64_t)env * L + (j + 1 - N)) * 2;
-    Ent s; s.x = l[0]; s.y = l[1]; s.vx = 0; s.vy = 0; ent[j + 1] = s;
+    sts4(sa_ent + (unsigned)(j + 1) * ES, l[0], l[1], (T)0, (T)0);
   }
   int t_now = p.t[env];
   const bool auto_reset = MODE == 2 && p.auto_reset != 0;
   int ep = auto_reset ? p.episode[env] : 0;
   const int ep0 = ep;
-  const T accel_m = wc.accel[ja], mass_m = wc.mass[ja], massinv_m = wc.mass_inv[ja], maxsp_m = wc.maxsp[ja];
+  const T accel_m = keep(wc.accel[ja]), mass_m = keep(wc.mass[ja]), massinv_m = keep(wc.mass_inv[ja]), maxsp_m = keep(wc.maxsp[ja]);
 
   // ---- slot bases (warp-uniform), offsets of this warp / this lane ------------------------------------
   const unsigned char* b_act = (const unsigned char*)p.actions;
@@ -180,13 +215,17 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   const bool role_on = lane < NPIECE && (!OBS || lane < 2 * PC4 || lane >= 2 * PC4 + 2 * PCT);
   // assign[i] = i never changes: both staging buffers get it once
   if (own) {
-    *(int32_t*)(wbase + lay.asg + (grp * N + j) * 4) = j;
-    *(int32_t*)(wbase + lay.buf + lay.asg + (grp * N + j) * 4) = j;
+    sts(sa_w + lay.asg + (unsigned)(grp * N + j) * 4u, j);
+    sts(sa_w + lay.buf + lay.asg + (unsigned)(grp * N + j) * 4u, j);
   }
 
   // action of my own agent, prefetched one step ahead
   const bool discrete = p.action_mode == GSM_ACT_DISCRETE;
-  const unsigned act_off = discrete ? ((unsigned)env * N + ja) * 4u : ((unsigned)env * N + ja) * 2u * (unsigned)RB;
+  const unsigned act_off = keep(discrete ? ((unsigned)env * N + ja) * 4u : ((unsigned)env * N + ja) * 2u * (unsigned)RB);
+  // 16-byte pieces of the idx / obs blocks: byte offsets of my piece in the slot and in the staging buffer
+  const unsigned n_idx = (lay.obs - lay.idx) / 16, n_obs = (lay.cnt - lay.obs) / 16;
+  const unsigned off_idx = keep(wrow0 * (unsigned)(K * 4) + (unsigned)lane * 16u), off_obs = keep(wrow0 * (unsigned)(GSM_OBS_DIM * RB) + (unsigned)lane * 16u);
+  const unsigned off_done = keep((unsigned)env * N + (unsigned)ja);
   int act_next = 0;
   T actx_next = 0, acty_next = 0;
   if (!OBS) {
@@ -201,7 +240,11 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   // in-kernel re-draw are prologues; every other pass is one env step.  One copy of the code serves both.
   bool pro = !OBS;
   int step = 0;
+  unsigned sb_off = 0;                                   // staging buffer of the next output step (0 / lay.buf)
+  const unsigned lrow0 = keep((unsigned)(grp * N * K));  // my env's first neighbour row inside the warp's block
   while (step < n_steps) {
+   // hot loop: runs until the launch ends or an env of the warp finishes its episode (MODE 2)
+   for (;;) {
     if (!OBS && !pro) {
       // ---- SPEC §2 + §4 for my own agent (lanes j >= N shadow agent 0 and publish nothing) -----------
       T ux = actx_next, uy = acty_next;
@@ -224,11 +267,11 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       mvx = nvx; mvy = nvy;
       mx = mx + nvx * p.dt; my = my + nvy * p.dt;
       t_now += 1;
-      if (own) { Ent s; s.x = mx; s.y = my; s.vx = mvx; s.vy = mvy; ent[j] = s; }
+      if (own) sts4(sa_ent + (unsigned)j * ES, mx, my, mvx, mvy);
       __syncwarp();
     }
     const bool st_on = !pro;                             // warp-uniform: this pass produces outputs
-    unsigned char* const sb = wbase + (step & 1) * lay.buf;
+    const unsigned sb = sa_w + sb_off;                   // this step's staging buffer
     // the bulk copy that read this buffer two steps ago must have finished reading it; the first
     // ballot below orders every lane's STS behind lane 0's wait
     if (st_on && bulk && lane == 0) bulk_wait_read<1>();
@@ -240,7 +283,9 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
 #pragma unroll
     for (int i = 0; i < N; i++) {
       const int e = e_hi - (j < i ? 1 : 0);
-      const Ent si = ent[i], so = ent[e];
+      Ent si, so;
+      lds4(sa_ent + (unsigned)i * ES, si.x, si.y, si.vx, si.vy);
+      lds4(sa_ent + (unsigned)e * ES, so.x, so.y, so.vx, so.vy);
       const T dx = so.x - si.x, dy = so.y - si.y;
       const T dist = A::sqrt(dx * dx + dy * dy);
       const T dmin = wc.size[i] + size_o;
@@ -252,12 +297,12 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       const int rank = __popc(bits & low_mask(j));
       const int pos = nb ? rank : cnt + (j - rank);
       if (has && pos < K && st_on) {
-        const unsigned lr = (unsigned)((grp * N + i) * K + pos);
-        *(int32_t*)(sb + lay.idx + lr * 4u) = nb ? e : -1;
-        T* f = (T*)(sb + lr * (unsigned)(GSM_NBR_FEAT_DIM * RB));
+        const unsigned lr = lrow0 + (unsigned)(i * K + pos);
+        sts(sb + lay.idx + lr * 4u, nb ? e : -1);
+        const unsigned f = sb + lr * (unsigned)(GSM_NBR_FEAT_DIM * RB);
         const T z = (T)0;
-        if (nb) { st2<T>(f, dx, dy); st2<T>(f + 2, so.vx - si.vx, so.vy - si.vy); st2<T>(f + 4, dist, type_o); }
-        else { st2<T>(f, z, z); st2<T>(f + 2, z, z); st2<T>(f + 4, z, z); }
+        if (nb) { sts2(f, dx, dy); sts2(f + 2 * RB, so.vx - si.vx, so.vy - si.vy); sts2(f + 4 * RB, dist, type_o); }
+        else { sts2(f, z, z); sts2(f + 2 * RB, z, z); sts2(f + 4 * RB, z, z); }
       }
       if (cnt > K) cnt = K;
       if (st_on && j < 3) {                               // lanes 0, 1, 2 stage cnt, adj, cost of agent i
@@ -266,11 +311,11 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         const unsigned ao = (unsigned)(grp * N + i);
         if (RB == 4) {                                    // three equal 4-byte blocks in a row: one store
           const unsigned v = j == 0 ? (unsigned)cnt : (j == 1 ? ebits : __float_as_uint((float)__popc(cbits)));
-          if (!OBS || j < 2) *(uint32_t*)(sb + lay.cnt + (unsigned)j * RS4 + ao * 4u) = v;
+          if (!OBS || j < 2) sts(sb + lay.cnt + (unsigned)j * RS4 + ao * 4u, v);
         } else {
-          if (j == 0) *(int32_t*)(sb + lay.cnt + ao * 4u) = cnt;
-          else if (j == 1) *(uint32_t*)(sb + lay.adj + ao * 4u) = ebits;
-          else if (!OBS) *(T*)(sb + lay.cost + ao * (unsigned)RB) = (T)__popc(cbits);
+          if (j == 0) sts(sb + lay.cnt + ao * 4u, cnt);
+          else if (j == 1) sts(sb + lay.adj + ao * 4u, ebits);
+          else if (!OBS) sts(sb + lay.cost + ao * (unsigned)RB, (T)__popc(cbits));
         }
       }
       if (j == N - 1 + i) { gxs = dx; gys = dy; gd = dist; }   // my landmark is this agent's goal
@@ -305,8 +350,8 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
 
     if (st_on) {
       // ---- per-agent outputs --------------------------------------------------------------------------
-      T* const sobs = (T*)(sb + lay.obs) + (unsigned)grp * (N * GSM_OBS_DIM);
-      if (own) { st2<T>(sobs + j * GSM_OBS_DIM, mvx, mvy); st2<T>(sobs + j * GSM_OBS_DIM + 2, mx, my); }
+      const unsigned sobs = sb + lay.obs + (unsigned)grp * (unsigned)(N * GSM_OBS_DIM * RB);
+      if (own) { sts2(sobs + (unsigned)j * (GSM_OBS_DIM * RB), mvx, mvy); sts2(sobs + (unsigned)j * (GSM_OBS_DIM * RB) + 2 * RB, mx, my); }
       T rs = ((T)0 - p.w_dist * gd) + (gd < p.goal_tol ? p.w_goal : (T)0);
       if (p.share_reward && !OBS) {
         T s = shfl(FULL, rs, shift + N - 1);
@@ -316,35 +361,37 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       }
       if (j >= N - 1 && j < 2 * N - 1) {
         const unsigned ao = (unsigned)(j - (N - 1));
-        st2<T>(sobs + ao * GSM_OBS_DIM + 4, gxs, gys);
-        if (!OBS) *(T*)(sb + lay.rew + ((unsigned)grp * N + ao) * (unsigned)RB) = rs;
+        sts2(sobs + ao * (GSM_OBS_DIM * RB) + 4 * RB, gxs, gys);
+        if (!OBS) sts(sb + lay.rew + ((unsigned)grp * N + ao) * (unsigned)RB, rs);
       }
-      if (!OBS && own && active) b_done[(unsigned)env * N + j] = (uint8_t)(t_now >= p.episode_length);
+      if (!OBS && own && active) b_done[off_done] = (uint8_t)(t_now >= p.episode_length);
       // ---- the staged blocks leave -----------------------------------------------------------------------
       if (bulk) {
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          bulk_store(b_feat + wrow0 * (unsigned)(K * GSM_NBR_FEAT_DIM * RB), sb, lay.idx);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       :: "l"(b_feat + wrow0 * (unsigned)(K * GSM_NBR_FEAT_DIM * RB)), "r"(sb), "r"(lay.idx) : "memory");
           bulk_commit();
         }
-        const unsigned n_idx = (lay.obs - lay.idx) / 16, n_obs = (lay.cnt - lay.obs) / 16;
-        V* const g_idx = (V*)(b_idx + wrow0 * (unsigned)(K * 4));
-        V* const g_obs = (V*)(b_obs + wrow0 * (unsigned)(GSM_OBS_DIM * RB));
-        const V* const s_idx = (const V*)(sb + lay.idx);
-        const V* const s_obs = (const V*)(sb + lay.obs);
-        if (lane < n_idx) g_idx[lane] = s_idx[lane];
-        if (lane + 32 < n_idx) g_idx[lane + 32] = s_idx[lane + 32];
-        if (lane < n_obs) g_obs[lane] = s_obs[lane];
-        if (lane + 32 < n_obs) g_obs[lane + 32] = s_obs[lane + 32];
-        if (role_on) *(V*)c_role = *(const V*)(sb + lay.cnt + lane * 16);
+        V* const g_idx = (V*)(b_idx + off_idx);
+        V* const g_obs = (V*)(b_obs + off_obs);
+        const unsigned s_idx = sb + lay.idx + (unsigned)lane * 16u, s_obs = sb + lay.obs + (unsigned)lane * 16u;
+        if (lane < n_idx) g_idx[0] = lds16(s_idx);
+        if (lane + 32 < n_idx) g_idx[32] = lds16(s_idx + 512);
+        if (lane < n_obs) g_obs[0] = lds16(s_obs);
+        if (lane + 32 < n_obs) g_obs[32] = lds16(s_obs + 512);
+        if (role_on) *(V*)c_role = lds16(sb + lay.cnt + (unsigned)lane * 16u);
       } else {
         // ragged / masked / unaligned warps: word-wise, per-env predicated
         __syncwarp();
         auto copy_words = [&](unsigned char* g, unsigned soff, unsigned bytes) {
           const unsigned wpe = bytes / (4 * EPW);         // words per env
           for (unsigned q = lane; q < bytes / 4; q += 32)
-            if ((act_bits >> ((q / wpe) * GW)) & 1u) ((uint32_t*)g)[q] = ((const uint32_t*)(sb + soff))[q];
+            if ((act_bits >> ((q / wpe) * GW)) & 1u) {
+              unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sb + soff + q * 4u) : "memory");
+              ((uint32_t*)g)[q] = v;
+            }
         };
         copy_words(b_feat + wrow0 * (unsigned)(K * GSM_NBR_FEAT_DIM * RB), lay.feat, lay.idx - lay.feat);
         copy_words(b_idx + wrow0 * (unsigned)(K * 4), lay.idx, lay.obs - lay.idx);
@@ -361,32 +408,37 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     }
     if (OBS) break;
     if (pro) { pro = false; continue; }                  // the prologue consumed no step
-
-    // ---- episode end inside a fused rollout: re-draw (terminal outputs stay in slot s) -----------------
-    if (MODE == 2 && auto_reset) {
-      const bool fin = t_now >= p.episode_length;
-      if (__any_sync(FULL, fin)) {
-        __syncwarp();                                     // every lane has read the old table
-        if (fin) {
-          const uint64_t genv = (uint64_t)(p.env_offset + env);
-          spawn_draw<T>(genv, ep, ja, p.seed, p.ext[GSM_ENT_AGENT], mx, my);
-          mvx = 0; mvy = 0;
-          if (own) { Ent s; s.x = mx; s.y = my; s.vx = 0; s.vy = 0; ent[j] = s; }
-          if (has && j + 1 >= N) {
-            Ent s; s.vx = 0; s.vy = 0;
-            spawn_draw<T>(genv, ep, j + 1, p.seed, p.ext[wc.eflag[j + 1] >> 1], s.x, s.y);
-            ent[j + 1] = s;
-          }
-          t_now = 0;
-          ep += 1;
-        }
-        __syncwarp();
-        pro = step + 1 < n_steps;                         // the new positions need their forces
-      }
-    }
     b_obs += ss.obs; b_idx += ss.nbr_idx; b_feat += ss.nbr_feat; b_done += ss.done;
     c_role += role_stride;
+    sb_off = lay.buf - sb_off;
     step++;
+    if (step >= n_steps) break;
+    if (MODE == 2 && auto_reset && __any_sync(FULL, t_now >= p.episode_length)) break;
+   }
+   if (OBS) break;
+   // ---- episode end inside a fused rollout: re-draw (the terminal outputs stay in their slot).  Cold:
+   //      outside the hot loop so that its calls and spills stay out of it ------------------------------------
+   if (MODE == 2 && auto_reset) {
+     const bool fin = t_now >= p.episode_length;
+     if (__any_sync(FULL, fin)) {
+       __syncwarp();                                      // every lane has read the old table
+       if (fin) {
+         const uint64_t genv = (uint64_t)(p.env_offset + env);
+         spawn_draw<T>(genv, ep, ja, p.seed, p.ext[GSM_ENT_AGENT], mx, my);
+         mvx = 0; mvy = 0;
+         if (own) sts4(sa_ent + (unsigned)j * ES, mx, my, (T)0, (T)0);
+         if (has && j + 1 >= N) {
+           T lx, ly;
+           spawn_draw<T>(genv, ep, j + 1, p.seed, p.ext[wc.eflag[j + 1] >> 1], lx, ly);
+           sts4(sa_ent + (unsigned)(j + 1) * ES, lx, ly, (T)0, (T)0);
+         }
+         t_now = 0;
+         ep += 1;
+       }
+       __syncwarp();
+       pro = step < n_steps;                              // the new positions need their forces
+     }
+   }
   }
   if (bulk && lane == 0) bulk_wait_read<0>();            // shared memory must outlive the copy that reads it
 
@@ -402,7 +454,9 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     }
     if (auto_reset && ep != ep0 && has && j + 1 >= N) {
       T* l = p.lm_pos + ((int64_t)env * L + (j + 1 - N)) * 2;
-      l[0] = ent[j + 1].x; l[1] = ent[j + 1].y;
+      T lx, ly, t0, t1;
+      lds4(sa_ent + (unsigned)(j + 1) * ES, lx, ly, t0, t1);
+      l[0] = lx; l[1] = ly;
     }
   }
 }

@@ -218,7 +218,7 @@ static int launch_wide_one(const HostParams& hp, const KParams<GSM_REAL>& kp, in
     if (e != cudaSuccess) return (int)e;
     attr_done[which] = true;
   }
-  k<<<(unsigned)grid, kWideThreads, smem, st>>>(kp, observe ? 1 : n_steps, ss, wc);
+  k<<<(unsigned)grid, kWideThreads, smem, st>>>(kp, observe ? 1 : n_steps, ss, wc, wide_smem_layout((int)sizeof(T), N, E, kp.K, EPW));
   return (int)cudaGetLastError();
 }
 
