@@ -181,7 +181,8 @@ static int launch_spec_one(const KParams<GSM_REAL>& kp, int n_steps, const StepS
 
 // ---- one-lane-per-other navigation kernel (gsm_kernels_wide.cuh) ---------------------------------
 // (N, L) instances; preferred over the (N*P lanes per env) specialised kernel where one exists.
-#define GSM_WIDE_TABLE(X) X(3, 6)
+// K: max_nbrs the instance is compiled for (0: any, read at run time)
+#define GSM_WIDE_TABLE(X) X(3, 6, 8) X(3, 6, 0)
 
 static bool has_wide(const HostParams& hp) {
   if (!spec_enabled() || env_int("GSM_NO_WIDE", 0) != 0 || env_int("GSM_SPEC_P", 0) != 0) return false;
@@ -190,13 +191,13 @@ static bool has_wide(const HostParams& hp) {
     if (hp.h_size[i] != hp.h_size[0] || (hp.h_eflag[i] & 1) != (hp.h_eflag[0] & 1)) return false;
   // 32-bit lane offsets into one slot of the largest output
   if (hp.n_envs * hp.N * hp.K * (int64_t)(GSM_NBR_FEAT_DIM * sizeof(GSM_REAL)) >= (1ll << 31)) return false;
-#define X(n, l) if (hp.N == n && hp.L == l) return true;
+#define X(n, l, k) if (hp.N == n && hp.L == l) return true;
   GSM_WIDE_TABLE(X)
 #undef X
   return false;
 }
 
-template <int N, int L>
+template <int N, int L, int KT>
 static int launch_wide_one(const HostParams& hp, const KParams<GSM_REAL>& kp, int n_steps, const StepStrides& ss,
                            bool observe, cudaStream_t st) {
   typedef GSM_REAL T;
@@ -209,7 +210,7 @@ static int launch_wide_one(const HostParams& hp, const KParams<GSM_REAL>& kp, in
   }
   const int64_t grid = (kp.n_envs + EPW * WPC - 1) / (EPW * WPC);
   const size_t smem = wide_smem_bytes((int)sizeof(T), N, E, kp.K, EPW);
-  auto k = observe ? env_wide_kernel<T, N, L, 1> : (kp.auto_reset ? env_wide_kernel<T, N, L, 2> : env_wide_kernel<T, N, L, 0>);
+  auto k = observe ? env_wide_kernel<T, N, L, 1, KT> : (kp.auto_reset ? env_wide_kernel<T, N, L, 2, KT> : env_wide_kernel<T, N, L, 0, KT>);
   static bool attr_done[3] = {false, false, false};      // per instance (this function is one per (T, N, L))
   const int which = observe ? 1 : (kp.auto_reset ? 2 : 0);
   if (!attr_done[which]) {
@@ -237,7 +238,7 @@ int GSM_SFX(launch_spec)(const HostParams& hp, const gsm_step_io& io, int n_step
   const bool one_stride = sizeof(GSM_REAL) != 4 || (ss.nbr_cnt == ss.adj && ss.adj == ss.reward && ss.reward == ss.cost &&
                                                     ss.cost == ss.assign);
   if (has_wide(hp) && one_stride) {
-#define X(n, l) if (hp.N == n && hp.L == l) return launch_wide_one<n, l>(hp, kp, n_steps, ss, observe != 0, st);
+#define X(n, l, k) if (hp.N == n && hp.L == l && (k == 0 || hp.K == k)) return launch_wide_one<n, l, k>(hp, kp, n_steps, ss, observe != 0, st);
     GSM_WIDE_TABLE(X)
 #undef X
   }
