@@ -199,8 +199,6 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   }
   int t_now = p.t[env];
   const bool auto_reset = MODE == 2 && p.auto_reset != 0;
-  int ep = auto_reset ? p.episode[env] : 0;
-  const int ep0 = ep;
   const T accel_m = keep(wc.accel[ja]), mass_m = keep(wc.mass[ja]), massinv_m = keep(wc.mass_inv[ja]), maxsp_m = keep(wc.maxsp[ja]);
 
   // ---- slot bases (warp-uniform), offsets of this warp / this lane ------------------------------------
@@ -251,7 +249,11 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   bool pro = !OBS;
   int step = 0;
   unsigned sb_off = 0;                                   // staging buffer of the next output step (0 / lay.buf)
-  const unsigned lrow0 = keep((unsigned)(grp * N * K));  // my env's first neighbour row inside the warp's block
+  // lane-constant parts of my staging addresses (feature rows, idx rows, scalar role, obs rows of my env)
+  const unsigned o_feat = keep((unsigned)(grp * N * K) * (unsigned)(GSM_NBR_FEAT_DIM * RB));
+  const unsigned o_idx = keep(lay.idx + (unsigned)(grp * N * K) * 4u);
+  const unsigned o_sc = keep(lay.cnt + (unsigned)(j < 3 ? j : 0) * (unsigned)RS4 + (unsigned)(grp * N) * 4u);
+  const unsigned o_obs = keep(lay.obs + (unsigned)grp * (unsigned)(N * GSM_OBS_DIM * RB));
   while (step < n_steps) {
    // hot loop: runs until the launch ends or an env of the warp finishes its episode (MODE 2)
    for (;;) {
@@ -282,6 +284,7 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     }
     const bool st_on = !pro;                             // warp-uniform: this pass produces outputs
     const unsigned sb = sa_w + sb_off;                   // this step's staging buffer
+    const unsigned a_feat = sb + o_feat, a_idx = sb + o_idx, a_sc = sb + o_sc, sobs = sb + o_obs;
     // the bulk copy that read this buffer two steps ago must have finished reading it; the first
     // ballot below orders every lane's STS behind lane 0's wait
     if (st_on && bulk && lane == 0) bulk_wait_read<1>();
@@ -307,9 +310,8 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       const int rank = __popc(bits & low_mask(j));
       const int pos = nb ? rank : cnt + (j - rank);
       if (has && pos < K && st_on) {
-        const unsigned lr = lrow0 + (unsigned)(i * K + pos);
-        sts(sb + lay.idx + lr * 4u, nb ? e : -1);
-        const unsigned f = sb + lr * (unsigned)(GSM_NBR_FEAT_DIM * RB);
+        sts(a_idx + (unsigned)pos * 4u + (unsigned)(i * K * 4), nb ? e : -1);
+        const unsigned f = a_feat + (unsigned)pos * (unsigned)(GSM_NBR_FEAT_DIM * RB) + (unsigned)(i * K * GSM_NBR_FEAT_DIM * RB);
         const T z = (T)0;
         if (nb) { sts2(f, dx, dy); sts2(f + 2 * RB, so.vx - si.vx, so.vy - si.vy); sts2(f + 4 * RB, dist, type_o); }
         else { sts2(f, z, z); sts2(f + 2 * RB, z, z); sts2(f + 4 * RB, z, z); }
@@ -321,7 +323,7 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         const unsigned ao = (unsigned)(grp * N + i);
         if (RB == 4) {                                    // three equal 4-byte blocks in a row: one store
           const unsigned v = j == 0 ? (unsigned)cnt : (j == 1 ? ebits : __float_as_uint((float)__popc(cbits)));
-          if (!OBS || j < 2) sts(sb + lay.cnt + (unsigned)j * RS4 + ao * 4u, v);
+          if (!OBS || j < 2) sts(a_sc + (unsigned)(i * 4), v);
         } else {
           if (j == 0) sts(sb + lay.cnt + ao * 4u, cnt);
           else if (j == 1) sts(sb + lay.adj + ao * 4u, ebits);
@@ -360,7 +362,6 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
 
     if (st_on) {
       // ---- per-agent outputs --------------------------------------------------------------------------
-      const unsigned sobs = sb + lay.obs + (unsigned)grp * (unsigned)(N * GSM_OBS_DIM * RB);
       if (own) { sts2(sobs + (unsigned)j * (GSM_OBS_DIM * RB), mvx, mvy); sts2(sobs + (unsigned)j * (GSM_OBS_DIM * RB) + 2 * RB, mx, my); }
       T rs = ((T)0 - p.w_dist * gd) + (gd < p.goal_tol ? p.w_goal : (T)0);
       if (p.share_reward && !OBS) {
@@ -433,7 +434,10 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
      if (__any_sync(FULL, fin)) {
        __syncwarp();                                      // every lane has read the old table
        if (fin) {
+         // the episode counter and the landmarks are not held in registers across the hot loop: both are
+         // read / written in global memory right here (once per episode)
          const uint64_t genv = (uint64_t)(p.env_offset + env);
+         const int ep = p.episode[env];
          spawn_draw<T>(genv, ep, ja, p.seed, p.ext[GSM_ENT_AGENT], mx, my);
          mvx = 0; mvy = 0;
          if (own) sts4(sa_ent + (unsigned)j * ES, mx, my, (T)0, (T)0);
@@ -441,10 +445,12 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
            T lx, ly;
            spawn_draw<T>(genv, ep, j + 1, p.seed, p.ext[wc.eflag[j + 1] >> 1], lx, ly);
            sts4(sa_ent + (unsigned)(j + 1) * ES, lx, ly, (T)0, (T)0);
+           if (active) { T* l = p.lm_pos + ((int64_t)env * L + (j + 1 - N)) * 2; l[0] = lx; l[1] = ly; }
          }
          t_now = 0;
-         ep += 1;
        }
+       __syncwarp();                                      // every lane of the env has read the old counter
+       if (fin && j == 0 && active) p.episode[env] += 1;
        __syncwarp();
        pro = step < n_steps;                              // the new positions need their forces
      }
@@ -458,16 +464,7 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       T* a = p.agent_state + ((int64_t)env * N + j) * 4;
       st2<T>(a, mx, my); st2<T>(a + 2, mvx, mvy);
     }
-    if (j == 0) {
-      p.t[env] = t_now;
-      if (auto_reset && ep != ep0) p.episode[env] = ep;
-    }
-    if (auto_reset && ep != ep0 && has && j + 1 >= N) {
-      T* l = p.lm_pos + ((int64_t)env * L + (j + 1 - N)) * 2;
-      T lx, ly, t0, t1;
-      lds4(sa_ent + (unsigned)(j + 1) * ES, lx, ly, t0, t1);
-      l[0] = lx; l[1] = ly;
-    }
+    if (j == 0) p.t[env] = t_now;
   }
 }
 
