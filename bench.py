@@ -430,11 +430,27 @@ def run_gpu(args):
     e2e_s = time.perf_counter() - t0
     stats.add(args.envs * Ke, N_AGENTS, float(rew.sum()), float(cost.sum()), float(done.sum()))
     h2d = host_acts[0].nbytes
-    d2h = sum(v.nbytes for k, v in vec.buf.items() if k != "actions")
+    d2h_dense = sum(v.nbytes for k, v in vec.buf.items() if k != "actions")
+    # bytes that actually cross PCIe per step in the default (sparse) mode: the dense small outputs plus the
+    # nbr_cnt valid rows of nbr_feat / nbr_idx (counted on the last step's nbr_cnt)
+    row_b = vec.buf["nbr_feat"].itemsize * vec.buf["nbr_feat"].shape[-1]
+    d2h = d2h_dense - vec.buf["nbr_feat"].nbytes + int(graph["nbr_cnt"].sum()) * row_b
+
+    def e2e_variant(n, **kw):
+        vec.set_host_outputs(**kw)
+        for s_ in range(3):
+            vec.step(host_acts[s_ % 8])
+        t1 = time.perf_counter()
+        for s_ in range(n):
+            vec.step(host_acts[s_ % 8])
+        return args.envs * N_AGENTS * n / (time.perf_counter() - t1)
+    e2e_dense = e2e_variant(max(10, Ke // 4), outputs=None, sparse=False)
+    lean = [k for k in vec.buf if k not in ("actions", "nbr_idx", "assign")]
+    e2e_lean = e2e_variant(max(10, Ke // 4), outputs=lean, sparse=True)
     vec.close()
     # the ceiling of that path on this box: one pinned D2H copy of the same size, nothing else
-    dsrc = torch.empty(d2h, dtype=torch.uint8, device=dev)
-    hdst = torch.empty(d2h, dtype=torch.uint8, pin_memory=True)
+    dsrc = torch.empty(d2h_dense, dtype=torch.uint8, device=dev)
+    hdst = torch.empty(d2h_dense, dtype=torch.uint8, pin_memory=True)
     for _ in range(3):
         hdst.copy_(dsrc, non_blocking=True)
     torch.cuda.synchronize()
@@ -442,7 +458,7 @@ def run_gpu(args):
     for _ in range(20):
         hdst.copy_(dsrc, non_blocking=True)
         torch.cuda.synchronize()
-    pcie_d2h_gbs = d2h * 20 / (time.perf_counter() - tp0) / 1e9
+    pcie_d2h_gbs = d2h_dense * 20 / (time.perf_counter() - tp0) / 1e9
     del dsrc, hdst
 
     cl_ms = [closed["ms"], closed["fused_actor"]["ms"]] if closed is not None else [0.0, 0.0]
@@ -486,19 +502,27 @@ def run_gpu(args):
             "env_steps_per_s": value / N_AGENTS,
             "clocks": clocks,
             "e2e": {"value": agents * Ke * world / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "api": "GraphVecEnv.step -> gsm_step_host (pinned arena; 1 H2D + 1 kernel + 1 D2H)",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "d2h_bytes_per_step_dense": d2h_dense,
+                    "steps": Ke,
+                    "api": "GraphVecEnv.step -> gsm_step_host (mapped pinned arena; 1 H2D copy + the step kernel + 2 "
+                           "export kernels that write every output into the host arrays over PCIe, sending only the "
+                           "nbr_cnt valid rows of nbr_feat; all nine host arrays bit-identical to the device tensors)",
                     "host_affinity": numa,
                     "bound": "PCIe D2H of the step's outputs",
                     "d2h_gbs_achieved": d2h * Ke / e2e_s / 1e9,
                     "d2h_gbs_ceiling": pcie_d2h_gbs,
-                    "ceiling_note": "one pinned cudaMemcpy D2H of d2h_bytes_per_step + sync, measured in this run "
-                                    "on rank 0 (the e2e step adds the H2D of the actions, the kernel and the "
-                                    "Python wrapper)"},
+                    "ceiling_note": "one pinned cudaMemcpy D2H of the DENSE outputs + sync, measured in this run "
+                                    "on rank 0 (the e2e step adds the H2D of the actions, the kernels and the "
+                                    "Python wrapper)",
+                    "dense_copy_variant": {"value": e2e_dense * world, "note": "rank 0 x world; gsm_set_host_outputs("
+                                           "sparse = 0): one dense D2H copy per step (the round-1 path)"},
+                    "lean_variant": {"value": e2e_lean * world, "note": "rank 0 x world; sparse, nbr_idx (redundant "
+                                     "with adj) and assign (the identity in navigation) switched off"}},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(),
-                         "kernel": f"gsm::env_steps_kernel<float, NAVIGATION, 3, 6, P={spec_p}, MODE=2 (auto-reset)>",
+                         "kernel": "gsm::env_wide_kernel<float, N=3, L=6, MODE=2 (auto-reset), K=8>" if not os.environ.get("GSM_NO_WIDE")
+                                   else f"gsm::env_steps_kernel<float, NAVIGATION, 3, 6, P={spec_p}, MODE=2 (auto-reset)>",
                          "how": "THE timed region itself (same events as `value`): algorithmic bytes of every fused "
                                 "launch in it (WorldConfig.bytes_fused: action + all outputs per step; agent state, "
                                 "landmarks and step counter once per launch) / region time, max over ranks",

@@ -106,6 +106,7 @@ SYMBOLS = {
     "gsm_set_episode": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "gsm_get_episode": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "gsm_host_io": (C.c_int, [_H, _IO]),
+    "gsm_set_host_outputs": (C.c_int, [_H, C.c_uint32, C.c_int32]),
     "gsm_reset_host": (C.c_int, [_H, C.c_uint64, C.c_void_p, C.c_int64, _IO]),
     "gsm_step_host": (C.c_int, [_H, _IO]),
     "gsm_observe_host": (C.c_int, [_H, _IO]),

@@ -68,6 +68,13 @@ struct gsm_env {
   size_t arena_off[IO_COUNT], arena_total = 0, arena_out_begin = 0;
   gsm_step_io d_io, h_io;
   uint8_t* d_mask = nullptr;
+  // sparse export (arena host path): the pinned arena is MAPPED; a kernel writes the step's outputs into it
+  // over PCIe and skips the padding rows of nbr_feat / nbr_idx (host rows >= cnt already hold 0 / -1)
+  unsigned char* h_arena_dev = nullptr;   // device address of h_arena
+  int32_t* d_prev_cnt = nullptr;          // [n_envs*N] neighbour rows the host copy currently holds per agent
+  int host_sparse = 1;                    // GSM_HOST_DENSE=1 / gsm_set_host_outputs(..., sparse = 0): one dense D2H copy instead
+  uint32_t host_out_mask = 0xffffffffu;   // bit k: output k (gsm_io index) is delivered to the host by the *_host calls
+  int host_resync = 1;                    // next arena copy-out is dense and re-bases d_prev_cnt
   // rollout graph cache (one entry)
   cudaGraphExec_t graph_exec = nullptr;
   int graph_steps = 0;
@@ -249,8 +256,13 @@ int ensure_host_path(gsm_env* h) {
   h->arena_total = o;
   GSM_CUDA(h, cudaMalloc((void**)&h->d_arena, o));
   GSM_CUDA(h, cudaMemset(h->d_arena, 0, o));
-  GSM_CUDA(h, cudaHostAlloc((void**)&h->h_arena, o, cudaHostAllocDefault));
+  GSM_CUDA(h, cudaHostAlloc((void**)&h->h_arena, o, cudaHostAllocMapped));
   std::memset(h->h_arena, 0, o);
+  GSM_CUDA(h, cudaHostGetDevicePointer((void**)&h->h_arena_dev, h->h_arena, 0));
+  GSM_CUDA(h, cudaMalloc((void**)&h->d_prev_cnt, (size_t)h->hp.n_envs * h->hp.N * 4 + 16));
+  GSM_CUDA(h, cudaMemset(h->d_prev_cnt, 0, (size_t)h->hp.n_envs * h->hp.N * 4 + 16));
+  if (const char* v = std::getenv("GSM_HOST_DENSE")) h->host_sparse = std::atoi(v) ? 0 : 1;
+  h->host_resync = 1;
   GSM_CUDA(h, cudaMalloc((void**)&h->d_mask, (size_t)h->hp.n_envs * h->hp.N + 16));
   for (int k = 0; k < IO_COUNT; k++) {
     io_set(h->d_io, k, h->d_arena + h->arena_off[k]);
@@ -265,11 +277,91 @@ bool is_arena_io(const gsm_env* h, const gsm_step_io& io) {
   return true;
 }
 
+// ---- sparse export kernels (arena host path) ---------------------------------------------------------
+// Of an agent's K neighbour rows only the first cnt are data: that block (cnt * row bytes, contiguous, at
+// the start of the agent's K-row block) is written to the mapped host arena in 8-byte pieces, bytes of rows
+// in [cnt, prev) — valid on the host from an earlier call — are cleared, rows >= max(cnt, prev) already hold
+// zeros there and are not touched.  A warp serves 4 agents per pass.
+// Measured on B200 / PCIe gen5 (profiles/micro/mapped_d2h*.cu, 49152 agents x 8 rows x 24 B): dense DMA of
+// nbr_feat 169 us; this kernel 116-121 us at 38-56 % valid rows (the link carries partial lines as small
+// packets, so time follows the agent count more than the bytes); the same with 16-byte pieces 176 us (kept
+// out); nbr_idx with 4-byte scattered writes cost +100 us per step, so it leaves dense with the small outputs.
+__global__ void export_rows_kernel(const int32_t* __restrict__ cnt, int32_t* __restrict__ prev,
+                                   const unsigned char* __restrict__ feat, unsigned char* __restrict__ h_feat,
+                                   int64_t rows, int row_bytes, int K) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int ab = K * row_bytes, ppa = ab / 8;                // bytes / 8-byte pieces per agent
+  for (int64_t a0 = w * 4; a0 < rows; a0 += nw * 4) {
+    for (int q = lane; q < 4 * ppa; q += 32) {
+      const int64_t a = a0 + q / ppa;
+      if (a >= rows) continue;
+      const int o = (q % ppa) * 8;                            // byte offset inside the agent's block
+      const size_t g = (size_t)a * ab + o;
+      if (o < cnt[a] * row_bytes) *(uint2*)(h_feat + g) = *(const uint2*)(feat + g);
+      else if (o < prev[a] * row_bytes) *(uint2*)(h_feat + g) = make_uint2(0u, 0u);
+    }
+    __syncwarp();
+    if (lane < 4 && a0 + lane < rows) prev[a0 + lane] = cnt[a0 + lane];
+  }
+}
+
+struct DenseCopies { const unsigned char* src[8]; unsigned char* dst[8]; unsigned long long n16[8]; int n; };
+__global__ void export_dense_kernel(const __grid_constant__ DenseCopies c) {
+  for (int k = 0; k < c.n; k++)
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < c.n16[k];
+         i += (unsigned long long)gridDim.x * blockDim.x)
+      ((uint4*)c.dst[k])[i] = ((const uint4*)c.src[k])[i];
+}
+
 // D2H of the outputs of a host-path call.
 int copy_out(gsm_env* h, const gsm_step_io& host_io, bool with_rcd) {
   if (is_arena_io(h, host_io)) {
-    GSM_CUDA(h, cudaMemcpyAsync(h->h_arena + h->arena_out_begin, h->d_arena + h->arena_out_begin,
-                                h->arena_total - h->arena_out_begin, cudaMemcpyDeviceToHost, h->stream));
+    const auto wanted = [&](int k) {
+      if (!(h->host_out_mask >> k & 1u)) return false;
+      return with_rcd || !(k == IO_REWARD || k == IO_COST || k == IO_DONE);
+    };
+    const int64_t rows = h->hp.n_envs * h->hp.N;
+    if (!h->host_sparse || h->host_resync) {
+      // dense: every delivered output in full (one copy when nothing is masked out)
+      if (h->host_out_mask == 0xffffffffu) {
+        GSM_CUDA(h, cudaMemcpyAsync(h->h_arena + h->arena_out_begin, h->d_arena + h->arena_out_begin,
+                                    h->arena_total - h->arena_out_begin, cudaMemcpyDeviceToHost, h->stream));
+      } else {
+        for (int k = IO_OBS; k < IO_COUNT; k++)
+          if (h->host_out_mask >> k & 1u)
+            GSM_CUDA(h, cudaMemcpyAsync(h->h_arena + h->arena_off[k], h->d_arena + h->arena_off[k], h->io_bytes[k],
+                                        cudaMemcpyDeviceToHost, h->stream));
+      }
+      GSM_CUDA(h, cudaMemcpyAsync(h->d_prev_cnt, h->d_io.nbr_cnt, (size_t)rows * 4, cudaMemcpyDeviceToDevice, h->stream));
+      h->host_resync = 0;
+    } else {
+      DenseCopies dc;
+      dc.n = 0;
+      for (int k = IO_OBS; k < IO_COUNT; k++) {
+        if (k == IO_NBR_FEAT || !wanted(k)) continue;
+        dc.src[dc.n] = h->d_arena + h->arena_off[k];
+        dc.dst[dc.n] = h->h_arena_dev + h->arena_off[k];
+        dc.n16[dc.n] = (h->io_bytes[k] + 15) / 16;            // sub-buffers are 256-byte aligned and padded
+        dc.n++;
+      }
+      if (wanted(IO_NBR_FEAT)) {
+        export_rows_kernel<<<296, 256, 0, h->stream>>>(h->d_io.nbr_cnt, h->d_prev_cnt, (const unsigned char*)h->d_io.nbr_feat,
+                                                       h->h_arena_dev + h->arena_off[IO_NBR_FEAT], rows, GSM_NBR_FEAT_DIM * h->rb, h->hp.K);
+        GSM_CUDA(h, cudaGetLastError());
+        h->launches += 1;
+      }
+      static const int dense_memcpy = std::getenv("GSM_HOST_DENSE_MEMCPY") ? std::atoi(std::getenv("GSM_HOST_DENSE_MEMCPY")) : 0;
+      if (dc.n && dense_memcpy) {                              // A/B: the copy engine instead of the kernel
+        for (int k = 0; k < dc.n; k++)
+          GSM_CUDA(h, cudaMemcpyAsync(h->h_arena + (dc.dst[k] - h->h_arena_dev), dc.src[k], dc.n16[k] * 16,
+                                      cudaMemcpyDeviceToHost, h->stream));
+      } else if (dc.n) {
+        export_dense_kernel<<<148, 256, 0, h->stream>>>(dc);
+        GSM_CUDA(h, cudaGetLastError());
+        h->launches += 1;
+      }
+    }
   } else {
     for (int k = IO_OBS; k < IO_COUNT; k++) {
       if (!with_rcd && (k == IO_REWARD || k == IO_COST || k == IO_DONE)) continue;
@@ -278,7 +370,7 @@ int copy_out(gsm_env* h, const gsm_step_io& host_io, bool with_rcd) {
         GSM_CUDA(h, cudaMemcpyAsync(dst, io_get(h->d_io, k), h->io_bytes[k], cudaMemcpyDeviceToHost, h->stream));
     }
   }
-  GSM_CUDA(h, cudaStreamSynchronize(h->stream));
+  GSM_CUDA(h, cudaStreamSynchronize(h->stream));      // (polling cudaStreamQuery instead: no measurable gain)
   return 0;
 }
 
@@ -407,6 +499,7 @@ int gsm_destroy(gsm_env* h) {
   for (void* p : h->dev_allocs) cudaFree(p);
   if (h->d_arena) cudaFree(h->d_arena);
   if (h->h_arena) cudaFreeHost(h->h_arena);
+  if (h->d_prev_cnt) cudaFree(h->d_prev_cnt);
   if (h->d_mask) cudaFree(h->d_mask);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -567,6 +660,16 @@ int gsm_host_io(gsm_env* h, gsm_step_io* out) {
   return GSM_OK;
 }
 
+int gsm_set_host_outputs(gsm_env* h, uint32_t out_mask, int32_t sparse) {
+  if (!h) return GSM_ERR_INVALID_ARG;
+  out_mask |= 1u << IO_ACTIONS;
+  out_mask |= ~((1u << IO_COUNT) - 1u);                      // unknown bits read as "on": 0xffffffff stays "everything"
+  if (out_mask != h->host_out_mask || (sparse != 0) != (h->host_sparse != 0)) h->host_resync = 1;
+  h->host_out_mask = out_mask;
+  h->host_sparse = sparse != 0;
+  return GSM_OK;
+}
+
 int gsm_reset_host(gsm_env* h, uint64_t seed, const uint8_t* mask, int64_t mask_stride,
                    const gsm_step_io* io) {
   if (!h) return GSM_ERR_INVALID_ARG;
@@ -597,6 +700,7 @@ int gsm_step_host(gsm_env* h, const gsm_step_io* io) {
   DeviceGuard guard(h->device);
   int st = ensure_host_path(h);
   if (st) return st;
+  // (letting the step kernel read the actions from the mapped arena instead of this copy: no measurable gain)
   GSM_CUDA(h, cudaMemcpyAsync(const_cast<void*>(h->d_io.actions), io->actions, h->io_bytes[IO_ACTIONS],
                               cudaMemcpyHostToDevice, h->stream));
   st = do_step(h, h->d_io, h->stream);

@@ -54,6 +54,21 @@ class GraphVecEnv:
     def _check(self, st):
         abi.check(self.lib, st, self._h)
 
+    _IO_ORDER = ("actions", "obs", "nbr_idx", "nbr_feat", "nbr_cnt", "adj", "reward", "cost", "done", "assign")
+
+    def set_host_outputs(self, outputs=None, sparse: bool = True):
+        """Which outputs the *_host calls deliver (None: all) and how (`gsm_set_host_outputs`):
+        sparse=True sends only the nbr_cnt valid rows of nbr_feat over PCIe (the host arrays
+        stay bit-identical to the device tensors), sparse=False is one dense D2H copy.  Outputs left out
+        keep whatever the host array held."""
+        mask = 0xFFFFFFFF
+        if outputs is not None:
+            unknown = set(outputs) - set(self._IO_ORDER)
+            if unknown:
+                raise ValueError(f"unknown outputs {sorted(unknown)}")
+            mask = sum(1 << self._IO_ORDER.index(k) for k in outputs) | 1
+        self._check(self.lib.gsm_set_host_outputs(self._h, mask, int(bool(sparse))))
+
     def seed(self, seed: int):
         self._seed = int(seed)
 

@@ -220,6 +220,18 @@ int gsm_get_episode(gsm_env* h, int32_t* episode, void* stream);
  * sub-buffer pointers).  Passing exactly these to the *_host calls makes a step one
  * H2D copy (actions) + one kernel + one D2H copy (all outputs). */
 int gsm_host_io(gsm_env* h, gsm_step_io* out);
+/* What the *_host calls deliver into the gsm_host_io buffers, and how.
+ * out_mask: bit k = deliver output k, k in the order of gsm_step_io (1 obs, 2 nbr_idx, 3 nbr_feat,
+ *   4 nbr_cnt, 5 adj, 6 reward, 7 cost, 8 done, 9 assign); a runner that reads the graph through
+ *   adj + nbr_feat can drop nbr_idx (redundant), navigation can drop assign (the identity).  Outputs
+ *   that are switched off keep whatever the host buffer held.  Default: all.
+ * sparse != 0 (default): the pinned arena is mapped and a kernel writes the outputs into it over
+ *   PCIe, sending only the nbr_cnt[i] valid rows of nbr_feat per agent (71 % of a dense step's
+ *   bytes are nbr_feat, about half of its rows are padding) — the padding rows of the host buffer
+ *   already hold zeros and rows that stop being valid are cleared, so the host arrays stay
+ *   bit-identical to the device tensors.  sparse == 0: one dense D2H copy per call.
+ * A change takes effect with a dense re-synchronisation on the next *_host call. */
+int gsm_set_host_outputs(gsm_env* h, uint32_t out_mask, int32_t sparse);
 int gsm_reset_host(gsm_env* h, uint64_t seed, const uint8_t* mask, int64_t mask_stride,
                    const gsm_step_io* io);
 int gsm_step_host(gsm_env* h, const gsm_step_io* io);

@@ -434,7 +434,7 @@ def test_rollout_graph_equals_sequential_steps_and_host_path():
         obs, graph, rew, cost, done, infos = vec.step(acts[t])
     for k in OUT_KEYS:
         assert (vec.buf[k] == _np(seq[-1])[k].view(vec.buf[k].dtype)).all(), k
-    assert vec.kernel_launches == T
+    assert vec.kernel_launches == T + 2 * (T - 1)          # T steps; every step after the dense first one: 2 export kernels
     env.close(); vec.close()
 
 
@@ -811,6 +811,55 @@ def test_translation_invariance_at_full_size(name, N, B, kw):
         np.testing.assert_allclose(a["obs"][..., 4:], b["obs"][..., 4:], rtol=0, atol=4e-15)
     assert (b["obs"][..., 2:4] - a["obs"][..., 2:4] == shift).all()
     assert a["nbr_cnt"].sum() > 0
+
+
+@pytest.mark.parametrize("name,N,dtype,B", [("navigation", 3, "f32", 1027), ("navigation", 12, "f32", 130),
+                                             ("polygon", 6, "f64", 65), ("navigation", 3, "f64", 33)])
+def test_host_sparse_export_is_bit_identical_to_dense_copy(name, N, dtype, B):
+    """gsm_set_host_outputs: the sparse export (a kernel writes only the nbr_cnt valid rows of nbr_feat
+    into the mapped arena, clears rows that stop being valid) against one dense D2H copy per call,
+    over steps, full and masked resets; then with outputs switched off and on again."""
+    from gs_marl_b200.env_wrappers import GraphVecEnv
+    cfg = make_cfg(name, N, dtype, episode_length=6)
+    a, b = GraphVecEnv(cfg, B, seed=3), GraphVecEnv(cfg, B, seed=3)
+    b.set_host_outputs(None, sparse=False)
+    rng = np.random.default_rng(B)
+
+    def same(keys=OUT_KEYS):
+        for k in keys:
+            assert a.buf[k].tobytes() == b.buf[k].tobytes(), (name, N, k)
+    a.reset(); b.reset()
+    same([k for k in OUT_KEYS if k not in ("reward", "cost", "done")])
+    for t in range(20):
+        acts = random_actions(cfg, rng, (B,))
+        a.step(acts); b.step(acts)
+        same()
+        if t % 6 == 5:
+            m = (rng.random(B) < 0.4).astype(np.uint8)
+            a.reset(m); b.reset(m)
+            same()
+        if t == 12:
+            a.reset(); b.reset()
+            same()
+    # rows beyond nbr_cnt really are padding on the host
+    cnt = a.buf["nbr_cnt"]
+    pad = np.arange(cfg.max_nbrs)[None, None, :] >= cnt[..., None]
+    assert (a.buf["nbr_idx"][pad] == -1).all() and (a.buf["nbr_feat"][pad] == 0).all()
+    # outputs switched off keep their old host contents, the others still match
+    keep_idx = a.buf["nbr_idx"].copy()
+    a.set_host_outputs([k for k in OUT_KEYS if k not in ("nbr_idx", "assign")])
+    for t in range(3):
+        acts = random_actions(cfg, rng, (B,))
+        a.step(acts); b.step(acts)
+    assert (a.buf["nbr_idx"] == keep_idx).all()
+    same([k for k in OUT_KEYS if k not in ("nbr_idx", "assign")])
+    a.set_host_outputs(None)                                   # back on: dense re-synchronisation, then sparse again
+    for t in range(3):
+        acts = random_actions(cfg, rng, (B,))
+        a.step(acts); b.step(acts)
+        same()
+    assert a.kernel_launches > b.kernel_launches               # the export kernels are counted
+    a.close(); b.close()
 
 
 def test_graph_vec_env_host_auto_reset():
