@@ -143,15 +143,171 @@ __device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int ba
   }
 }
 
+// ---- round 2: the same solver with a leaner lockstep iteration -------------------------------------------
+// lsa_group spends 165 instructions per Dijkstra iteration (profiles/ncu_r2_team_polygon12_lines.txt): select
+// chains that index per-lane register arrays with a run-time index (u[il], r4c[jl], path[jl]: 16), the relax
+// step behind divergent branches (38), tie keys rebuilt from scratch (22), boolean arrays (22), index splits by
+// A (11).  Here everything that is addressed by a run-time index — u, row4col, col4row, path and, after the
+// search, the shortest-path costs — lives in the env's shared-memory block and is read with one LDS (group-
+// uniform address: a broadcast); the sets SR / SC are N-bit masks that every lane of the group carries
+// redundantly (i and j are group-uniform); the relax step is branch-free (a finished group runs with
+// minval = +inf, which can update nothing); the tie key of a column (unassigned: 64 + pos, assigned: 31 - pos,
+// column in the low bits) is kept in a register and touched only when its position or status changes.
+// Scan order and tie rule are lsa_group's, i.e. scipy's.
+struct TeamLsaSmem { int u, spc, r4c, c4r, path, words; };      // word offsets inside the env's solver block
+__host__ __device__ constexpr TeamLsaSmem team_lsa_smem(int rb, int N) {
+  TeamLsaSmem t{};
+  int o = 0;
+  t.u = o; o += N * rb / 4;
+  t.spc = o; o += N * rb / 4;
+  t.r4c = o; o += N;
+  t.c4r = o; o += N;
+  t.path = o; o += N;
+  t.words = o;
+  return t;
+}
+
+template <typename T, int N, int G, int GP>
+__device__ __forceinline__ void lsa_group2(const T* __restrict__ C, uint32_t* __restrict__ ws, int g, int base,
+                                           bool grp_live, int (&c4r_out)[N / G]) {
+  constexpr int A = N / G;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr TeamLsaSmem L = team_lsa_smem((int)sizeof(T), N);
+  const bool live = grp_live && g < G;
+  const T INF = r_inf<T>();
+  T* const su = (T*)(ws + L.u);
+  T* const sspc = (T*)(ws + L.spc);
+  int* const sr4c = (int*)(ws + L.r4c);
+  int* const sc4r = (int*)(ws + L.c4r);
+  int* const spath = (int*)(ws + L.path);
+  const int col0 = (g < G ? g : 0) * A;                   // my first column / row
+  const T* Cg = C + col0;
+  T v[A], spc[A];
+  int path[A], pos[A], keyp[A];
+  bool asg[A];                                            // my column is assigned (row4col != -1)
+#pragma unroll
+  for (int a = 0; a < A; a++) {
+    v[a] = 0; asg[a] = false; path[a] = -1;
+    if (live) { su[col0 + a] = 0; sr4c[col0 + a] = -1; sc4r[col0 + a] = -1; }
+  }
+  __syncwarp();
+  for (int cur = 0; cur < N; cur++) {
+    T minval = 0;
+    int i = cur, nrem = N, sink = grp_live ? -1 : 0;
+    unsigned SR = 0, SC = 0;                              // group-uniform
+    unsigned inr = live ? low_mask(A) : 0u;               // my columns still in scipy's `remaining`
+#pragma unroll
+    for (int a = 0; a < A; a++) {
+      spc[a] = INF; pos[a] = N - 1 - (col0 + a);
+      keyp[a] = ((asg[a] ? 31 - pos[a] : 64 + pos[a]) << 6) | (col0 + a);
+    }
+    for (int iter = 0; iter < N && __any_sync(FULL, sink == -1); iter++) {
+      const bool run = sink == -1;
+      if (run) SR |= 1u << i;
+      const T u_i = su[i];
+      const T mv = run ? minval : INF;                    // a finished group relaxes nothing
+      const T* Ci = Cg + i * N;
+      T lo = INF;
+#pragma unroll
+      for (int a = 0; a < A; a++) {
+        const T r = mv + Ci[a] - u_i - v[a];
+        const bool in_a = (inr >> a) & 1u;
+        const bool upd = in_a && r < spc[a];
+        spc[a] = upd ? r : spc[a];
+        path[a] = upd ? i : path[a];
+        const T cand = in_a ? spc[a] : INF;
+        lo = cand < lo ? cand : lo;
+      }
+#pragma unroll
+      for (int m = GP / 2; m >= 1; m >>= 1) {
+        const T o = __shfl_xor_sync(FULL, lo, m);
+        lo = o < lo ? o : lo;
+      }
+      // tie rule: an unassigned minimum with the largest position wins, else the minimum with the smallest
+      // position; positions are unique, the column index rides in the low bits of the key
+      int best = -1;
+#pragma unroll
+      for (int a = 0; a < A; a++) {
+        const int packed = (((inr >> a) & 1u) && spc[a] == lo) ? keyp[a] : -1;
+        best = packed > best ? packed : best;
+      }
+#pragma unroll
+      for (int m = GP / 2; m >= 1; m >>= 1) {
+        const int o = __shfl_xor_sync(FULL, best, m);
+        best = o > best ? o : best;
+      }
+      const int key = best >> 6, j = best < 0 ? 0 : (best & 63);
+      const int selpos = key >= 64 ? key - 64 : 31 - key;
+      const int r4c_j = sr4c[j];
+      if (run && best >= 0) {
+        minval = lo;
+        if (r4c_j == -1) sink = j; else i = r4c_j;
+        nrem--;
+        SC |= 1u << j;
+#pragma unroll
+        for (int a = 0; a < A; a++) {
+          if (col0 + a == j) inr &= ~(1u << a);
+          if (((inr >> a) & 1u) && pos[a] == nrem) {
+            pos[a] = selpos;
+            keyp[a] = ((asg[a] ? 31 - selpos : 64 + selpos) << 6) | (col0 + a);
+          }
+        }
+      }
+    }
+    // dual update (col4row as it was before this augmentation); the shortest-path costs and predecessors
+    // of my columns go to shared memory for the indexed reads
+#pragma unroll
+    for (int a = 0; a < A; a++) if (live) { sspc[col0 + a] = spc[a]; spath[col0 + a] = path[a]; }
+    __syncwarp();
+#pragma unroll
+    for (int a = 0; a < A; a++) {
+      const int row = col0 + a;
+      if (live && ((SR >> row) & 1u)) {
+        const int c = sc4r[row];
+        su[row] += row == cur ? minval : minval - sspc[c < 0 ? 0 : c];
+      }
+      if ((SC >> (col0 + a)) & 1u) v[a] -= minval - spc[a];
+    }
+    __syncwarp();
+    // augment along the path (every lane of the group walks it redundantly; lane 0 writes)
+    int j = sink < 0 ? 0 : sink;
+    bool going = grp_live && sink >= 0;
+    for (int iter = 0; iter < N && __any_sync(FULL, going); iter++) {
+      int arow = spath[j];
+      arow = arow < 0 ? 0 : arow;
+      const int tprev = sc4r[arow];
+      __syncwarp();                                       // all lanes of the group have read before lane 0 writes
+      if (going) {
+        if (g == 0) { sr4c[j] = arow; sc4r[arow] = j; }
+        j = tprev < 0 ? 0 : tprev;
+        if (arow == cur) going = false;
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int a = 0; a < A; a++) asg[a] = live && sr4c[col0 + a] != -1;
+  }
+#pragma unroll
+  for (int a = 0; a < A; a++) c4r_out[a] = live ? sc4r[col0 + a] : -1;
+}
+
+#ifndef GSM_TEAM_LSA2          // A/B: 1 = lsa_group2 (shared-memory solver state), 0 = lsa_group (registers)
+#define GSM_TEAM_LSA2 1
+#endif
+
 constexpr int kTeamThreads = 128;
 
 __host__ __device__ inline size_t team_env_bytes(int rb, int N) {
-  // per env: agent positions + velocities, N x N costs, shared-reward scratch
-  return ((size_t)(4 * N + N * N + N) * rb + 15) / 16 * 16;
+  // per env: agent positions + velocities, N x N costs, shared-reward scratch, solver block (lsa_group2)
+  return ((size_t)(4 * N + N * N + N) * rb + (size_t)team_lsa_smem(rb, N).words * 4 + 15) / 16 * 16;
 }
 
+#ifndef GSM_TEAM_BLOCKS        // A/B: resident CTAs per SM the fp32 instances are compiled for (4 -> 128 registers)
+#define GSM_TEAM_BLOCKS 4
+#endif
+template <typename T> struct TeamMinBlocks { static constexpr int value = sizeof(T) == 4 ? GSM_TEAM_BLOCKS : 1; };
 template <typename T, int SCN, int N, int G, int GP>
-__global__ void __launch_bounds__(kTeamThreads)
+__global__ void __launch_bounds__(kTeamThreads, TeamMinBlocks<T>::value)
 env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
                 const __grid_constant__ StepStrides ss) {
   constexpr int A = N / G, EPW = 32 / GP, L = SCN == GSM_SCN_POLYGON ? 1 : 2, E = N + L;
@@ -286,7 +442,11 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     }
     __syncwarp();
     int c4r[A];
+#if GSM_TEAM_LSA2
+    lsa_group2<T, N, G, GP>(cmat, (uint32_t*)(rsm + N), g, base, true, c4r);
+#else
     lsa_group<T, N, G, GP>(cmat, g, base, true, c4r);
+#endif
     __syncwarp();
 
     // ---- padding first: the rows of this warp's envs are one contiguous region -------------------
