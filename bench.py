@@ -316,6 +316,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     K, W, T = args.steps, args.warmup, args.rollout_t
+    sampler = ClockSampler(local); sampler.start()
     spec_p = os.environ.get("GSM_SPEC_P", "4 (default)")
     cfg = scenarios.load("navigation").make_world(N_AGENTS, dtype="f32", episode_length=EPISODE_LEN)
     env = MultiAgentGraphConstrainEnv(cfg, args.envs, device=local, env_offset=rank * args.envs, seed=1)
@@ -341,11 +342,16 @@ def run_gpu(args):
     # region lasts >= --region-ms whatever K is; envs are re-drawn in-kernel every EPISODE_LEN
     # steps (state and episode counters persist across replays); all nine outputs are written.
     region = RolloutRegion(sh_env, acts, ring, K, T, auto_reset=True)
-    sampler = ClockSampler(local); sampler.start()
     warm_units = max(1, -(-max(W, 3) // (region.regions_per_unit * K)))
     for _ in range(warm_units):
         region.replay_unit()
     torch.cuda.synchronize()
+    # the clock sampler was started first thing in this function; on a busy host (8 ranks, 8 nvidia-smi
+    # processes) its first sample can take seconds: keep the GPU under load until it reports (bounded)
+    t_wait = time.time()
+    while not sampler.lines and time.time() - t_wait < 15.0:
+        region.replay_unit()
+        torch.cuda.synchronize()
     units = torch.tensor([region.calibrate(args.region_ms)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(units, op=dist.ReduceOp.MAX)           # every rank runs the same work
