@@ -248,7 +248,10 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   // in-kernel re-draw are prologues; every other pass is one env step.  One copy of the code serves both.
   bool pro = !OBS;
   int step = 0;
-  unsigned sb_off = 0;                                   // staging buffer of the next output step (0 / lay.buf)
+  // staging buffer of the next output step: a loop-CARRIED address flipped by +-lay.buf (ptxas re-derives
+  // `sa_w + offset` at every use when it can; it cannot re-derive a carried value)
+  unsigned sb = sa_w;
+  int sb_delta = (int)lay.buf;
   // lane-constant parts of my staging addresses (feature rows, idx rows, scalar role, obs rows of my env)
   const unsigned o_feat = keep((unsigned)(grp * N * K) * (unsigned)(GSM_NBR_FEAT_DIM * RB));
   const unsigned o_idx = keep(lay.idx + (unsigned)(grp * N * K) * 4u);
@@ -283,7 +286,6 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       __syncwarp();
     }
     const bool st_on = !pro;                             // warp-uniform: this pass produces outputs
-    const unsigned sb = sa_w + sb_off;                   // this step's staging buffer
     const unsigned a_feat = sb + o_feat, a_idx = sb + o_idx, a_sc = sb + o_sc, sobs = sb + o_obs;
     // the bulk copy that read this buffer two steps ago must have finished reading it; the first
     // ballot below orders every lane's STS behind lane 0's wait
@@ -421,7 +423,8 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     if (pro) { pro = false; continue; }                  // the prologue consumed no step
     b_obs += ss.obs; b_idx += ss.nbr_idx; b_feat += ss.nbr_feat; b_done += ss.done;
     c_role += role_stride;
-    sb_off = lay.buf - sb_off;
+    sb += sb_delta;
+    sb_delta = -sb_delta;
     step++;
     if (step >= n_steps) break;
     if (MODE == 2 && auto_reset && __any_sync(FULL, t_now >= p.episode_length)) break;
