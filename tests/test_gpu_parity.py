@@ -813,6 +813,96 @@ def test_translation_invariance_at_full_size(name, N, B, kw):
     assert a["nbr_cnt"].sum() > 0
 
 
+WIDE_VARIANTS = [{}, {"share_reward": True}, {"own_goal_always": False}, {"cost_obstacles": False},
+                 {"action_mode": "continuous"}, {"max_nbrs": 4}, {"max_nbrs": 5, "share_reward": True},
+                 {"sensing_radius": 0.4}, {"sensing_radius": 3.0, "max_nbrs": 8}]
+
+
+@pytest.mark.parametrize("kw", WIDE_VARIANTS)
+@pytest.mark.parametrize("B", [1, 3, 130, 257])
+def test_wide_kernel_variants_f64(kw, B):
+    """env_wide_kernel (navigation-3: one lane per other entity, shared-memory entity table, staged outputs,
+    bulk copies) on every scenario switch, on max_nbrs below / at the number of others (the run-time-K
+    instance and the K = 8 instance), and on ragged batches (warps with 1..3 of 4 envs take the word-wise
+    copy path): fused 25 steps with in-kernel auto-reset, single steps and observe against the oracle."""
+    from oracle import gsm_oracle as O
+    cfg = make_cfg("navigation", 3, "f64", episode_length=7, **kw)
+    seed, T = 5 + B, 25
+    o = O.OracleEnv(cfg, B)
+    o.reset(seed)
+    o.agent_state[..., :2] *= 0.45                             # squeezed: contacts from the first step on
+    o.landmark_pos *= 0.45
+    o.step_count[:] = np.arange(B) % 7                         # staggered episode ends
+    env = _env(cfg, B, seed=seed)
+    env.reset()
+    env.set_state(o.agent_state, o.landmark_pos, o.step_count)
+    obs, graph = env.observe()
+    assert_match({**_np(graph), "obs": obs.cpu().numpy()}, o.observe(), rtol=F64_RTOL, atol=F64_ATOL,
+                 ctx=f"wide {kw} observe", keys=("obs", "nbr_idx", "nbr_feat", "nbr_cnt", "adj"))
+    acts = random_actions(cfg, np.random.default_rng(B), (T, B))
+    launches0 = env.kernel_launches
+    roll = _np(env.rollout(acts, auto_reset=True))
+    assert env.kernel_launches - launches0 == 1                 # ONE fused launch
+    total_cost = 0.0
+    for t in range(T):
+        want = {k: v.copy() for k, v in o.step(acts[t]).items()}
+        assert_match({k: roll[k][t] for k in OUT_KEYS}, want, rtol=F64_RTOL, atol=F64_ATOL, ctx=f"wide {kw} B={B} t={t}")
+        total_cost += want["cost"].sum()
+        if want["done"].any():
+            o.reset(seed, want["done"][:, 0].copy())
+    ag, lm, tt = env.get_state()
+    np.testing.assert_allclose(ag.cpu().numpy(), o.agent_state, rtol=F64_RTOL, atol=F64_ATOL)
+    assert (lm.cpu().numpy() == o.landmark_pos).all() and (tt.cpu().numpy() == o.step_count).all()
+    if B >= 130:
+        assert total_cost > 0, "case never exercised a collision"
+    # single steps after the rollout (the one-step instance of the same kernel)
+    for t in range(3):
+        a1 = random_actions(cfg, np.random.default_rng(100 + t), (B,))
+        want = o.step(a1)
+        env.step(a1)
+        assert_match(_np(env.buf), want, rtol=F64_RTOL, atol=F64_ATOL, ctx=f"wide {kw} single step {t}")
+    env.close()
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_wide_kernel_equals_spec_kernel_and_unaligned_buffers(dtype, monkeypatch):
+    """The wide kernel against the kernel it replaced (GSM_NO_WIDE=1 -> env_steps_kernel) on the same states
+    and actions: integer outputs identical, reals to rounding (the pair forces are summed in another order);
+    then the same rollout into output tensors that start 4 / 8 bytes off a 16-byte boundary (no bulk copies:
+    the word-wise path) — bit-identical to the aligned run."""
+    cfg = make_cfg("navigation", 3, dtype, episode_length=9)
+    B, T = 515, 20
+    rng = np.random.default_rng(1)
+    acts = random_actions(cfg, rng, (T, B))
+    a = _env(cfg, B, seed=2); a.reset()
+    ra = {k: v.clone() for k, v in a.rollout(acts, auto_reset=True).items()}
+    a.close()
+    # unaligned outputs: every tensor is a view that starts one element into a larger allocation
+    c = _env(cfg, B, seed=2); c.reset()
+    out = {}
+    for k in c.OUTPUTS:
+        full = c._alloc(k, (T,))
+        big = torch.zeros(full.numel() + 8, dtype=full.dtype, device=full.device)
+        out[k] = big[1:1 + full.numel()].view(full.shape)
+        assert out[k].data_ptr() % 16 != 0 or out[k].element_size() >= 16
+    rb = c.rollout(acts, out=out, auto_reset=True)
+    for k in OUT_KEYS:
+        assert torch.equal(ra[k], rb[k]), (k, "unaligned buffers")
+    c.close()
+    monkeypatch.setenv("GSM_NO_WIDE", "1")
+    b = _env(cfg, B, seed=2); b.reset()
+    rs = b.rollout(acts, auto_reset=True)
+    tol = dict(rtol=1e-4, atol=2e-5) if dtype == "f32" else dict(rtol=F64_RTOL, atol=F64_ATOL)
+    ga, gs = _np(ra), _np(rs)
+    if dtype == "f64":
+        assert_match({k: ga[k] for k in OUT_KEYS}, {k: gs[k] for k in OUT_KEYS}, ctx="wide vs spec", **tol)
+    else:                                                       # fp32: compare the first steps, before rounding differences grow at contacts
+        for k in ("nbr_cnt", "adj", "done", "assign"):
+            assert (ga[k][:2] == gs[k][:2]).mean() > 0.999, k
+        np.testing.assert_allclose(ga["obs"][:2], gs["obs"][:2], **tol)
+    b.close()
+
+
 @pytest.mark.parametrize("name,N,dtype,B", [("navigation", 3, "f32", 1027), ("navigation", 12, "f32", 130),
                                              ("polygon", 6, "f64", 65), ("navigation", 3, "f64", 33)])
 def test_host_sparse_export_is_bit_identical_to_dense_copy(name, N, dtype, B):
