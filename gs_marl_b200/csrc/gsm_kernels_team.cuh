@@ -501,9 +501,14 @@ __host__ __device__ inline size_t team_env_bytes(int rb, int N) {
 #ifndef GSM_TEAM_BLOCKS        // A/B: resident CTAs per SM the fp32 instances are compiled for (4 -> 128 registers)
 #define GSM_TEAM_BLOCKS 4
 #endif
-template <typename T> struct TeamMinBlocks { static constexpr int value = sizeof(T) == 4 ? GSM_TEAM_BLOCKS : 1; };
+#ifndef GSM_TEAM_BLOCKS_A1     // ... of the one-agent-per-lane instances (measured: 7 -> 64 registers is slower than 4 -> 122)
+#define GSM_TEAM_BLOCKS_A1 4
+#endif
+template <typename T, int A> struct TeamMinBlocks {
+  static constexpr int value = sizeof(T) != 4 ? 1 : (A == 1 ? GSM_TEAM_BLOCKS_A1 : GSM_TEAM_BLOCKS);
+};
 template <typename T, int SCN, int N, int G, int GP>
-__global__ void __launch_bounds__(kTeamThreads, TeamMinBlocks<T>::value)
+__global__ void __launch_bounds__(kTeamThreads, TeamMinBlocks<T, N / G>::value)
 env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
                 const __grid_constant__ StepStrides ss) {
   constexpr int A = N / G, EPW = 32 / GP, L = SCN == GSM_SCN_POLYGON ? 1 : 2, E = N + L;
