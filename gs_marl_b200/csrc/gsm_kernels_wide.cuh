@@ -8,9 +8,11 @@
 // This kernel turns the layout by 90 degrees:
 //   * an env owns GW = pow2(M) lanes; lane j is "other number j" of EVERY agent, the agents are the
 //     (unrolled) chunks.  M = 8 fills a warp with 4 envs and all 32 lanes;
-//   * every lane keeps the state of all N agents in registers and integrates all of them
-//     redundantly: no shuffle ever fetches a position, lanes j >= N-1 see the same landmark in every
-//     chunk and keep just that one;
+//   * the env's entities live in a shared-memory table (x, y, vx, vy): lane a < N OWNS agent a — it
+//     alone integrates it (state in registers) and publishes it with one 16-byte store; a chunk reads
+//     agent i and "its other" with two 16-byte loads.  No shuffle fetches a position, no select chain
+//     picks one out of per-lane copies (the first version kept all agents in every lane: 75 of its
+//     725 instructions per warp-step were that select chain);
 //   * one ballot per agent covers its whole neighbourhood (all 4 envs at once), so the row of a
 //     pair is known right after its own chunk — no second pass, no feature registers held;
 //   * the contact force of step s+1 is a function of exactly the pair geometry the graph pass of
@@ -19,9 +21,13 @@
 //     and after an in-kernel re-draw only;
 //   * lane N-1+i holds agent i's own goal as its landmark, so its chunk-i geometry IS the goal
 //     vector and the goal distance: reward and the goal half of obs cost no extra arithmetic;
-//   * per-agent constants (size, mass, accel, max_speed, flags) travel in the kernel parameter
-//     space and are compile-time indexed: constant-bank operands, no registers.
-// Everything else — arithmetic policy, output layout, auto-reset draws — is env_steps_kernel's.
+//   * per-agent constants (size, mass, accel, max_speed, flags) and the staging layout travel in the
+//     kernel parameter space; lane constants are chunk-independent (the launcher requires alike
+//     agents) and pinned with a self-shuffle so that ptxas cannot rebuild them inside the step loop;
+//   * every output of a warp-step is staged in shared memory and leaves as one bulk copy (nbr_feat)
+//     plus coalesced 16-byte pieces (see WideSmem below).
+// Arithmetic policy, output layout and auto-reset draws are env_steps_kernel's (fp32 softplus: SPEC §9
+// deviation 6).  History and measurements: profiles/README.md, round 2.
 #pragma once
 #include "gsm_kernels_spec.cuh"
 #include "gsm_kernels_big.cuh"   // bulk-store helpers
