@@ -27,7 +27,8 @@ for name, kw in (("dense", dict(outputs=None, sparse=False)), ("sparse_all", dic
                  ("sparse_no_idx_assign", dict(outputs=[k for k in outs if k not in ("nbr_idx", "assign")], sparse=True)),
                  ("sparse_feat_only", dict(outputs=["nbr_feat"], sparse=True)),
                  ("sparse_no_feat", dict(outputs=[k for k in outs if k != "nbr_feat"], sparse=True)),
-                 ("dense_no_feat", dict(outputs=[k for k in outs if k != "nbr_feat"], sparse=False))):
+                 ("dense_no_feat", dict(outputs=[k for k in outs if k != "nbr_feat"], sparse=False)),
+                 ("no_outputs", dict(outputs=[], sparse=True)), ("done_only", dict(outputs=["done"], sparse=True))):
     vec.set_host_outputs(**kw)
     for s in range(10):
         vec.step(acts[s % 8])
