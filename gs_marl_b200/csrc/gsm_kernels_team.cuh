@@ -501,8 +501,8 @@ __host__ __device__ inline size_t team_env_bytes(int rb, int N) {
 #ifndef GSM_TEAM_BLOCKS        // A/B: resident CTAs per SM the fp32 instances are compiled for (4 -> 128 registers)
 #define GSM_TEAM_BLOCKS 4
 #endif
-#ifndef GSM_TEAM_BLOCKS_A1     // ... of the one-agent-per-lane instances (measured: 7 -> 64 registers is slower than 4 -> 122)
-#define GSM_TEAM_BLOCKS_A1 4
+#ifndef GSM_TEAM_BLOCKS_A1     // ... of the one-agent-per-lane instances (N = 6, polygon, one launch / 4 streams: 4 CTAs 22.4 /
+#define GSM_TEAM_BLOCKS_A1 5   //     16.1 us, 5 CTAs 17.9 / 16.4, 6 CTAs 19.6 / 17.9, 7 CTAs 23.0 / 21.2)
 #endif
 template <typename T, int A> struct TeamMinBlocks {
   static constexpr int value = sizeof(T) != 4 ? 1 : (A == 1 ? GSM_TEAM_BLOCKS_A1 : GSM_TEAM_BLOCKS);

@@ -318,16 +318,17 @@ int GSM_SFX(launch_lane)(const HostParams& hp, const gsm_step_io& io, int n_step
 // GSM_TEAM_G picks another compiled one.
 #define GSM_TEAM_TABLE(X)                                                                     \
   X(GSM_SCN_POLYGON, 3, 1, 1) X(GSM_SCN_POLYGON, 4, 2, 2) X(GSM_SCN_POLYGON, 5, 1, 1)           \
-  X(GSM_SCN_POLYGON, 6, 3, 4) X(GSM_SCN_POLYGON, 6, 2, 2) X(GSM_SCN_POLYGON, 12, 4, 4)          \
-  X(GSM_SCN_POLYGON, 12, 6, 8) X(GSM_SCN_POLYGON, 6, 6, 8)                                      \
+  X(GSM_SCN_POLYGON, 6, 6, 8) X(GSM_SCN_POLYGON, 6, 3, 4) X(GSM_SCN_POLYGON, 6, 2, 2)           \
+  X(GSM_SCN_POLYGON, 12, 4, 4) X(GSM_SCN_POLYGON, 12, 6, 8)                                     \
   X(GSM_SCN_LINE, 3, 1, 1) X(GSM_SCN_LINE, 4, 2, 2) X(GSM_SCN_LINE, 5, 1, 1)                    \
-  X(GSM_SCN_LINE, 6, 3, 4) X(GSM_SCN_LINE, 6, 2, 2) X(GSM_SCN_LINE, 12, 4, 4)                   \
-  X(GSM_SCN_LINE, 12, 6, 8) X(GSM_SCN_LINE, 6, 6, 8)
+  X(GSM_SCN_LINE, 6, 6, 8) X(GSM_SCN_LINE, 6, 3, 4) X(GSM_SCN_LINE, 6, 2, 2)                    \
+  X(GSM_SCN_LINE, 12, 4, 4) X(GSM_SCN_LINE, 12, 6, 8)
 // measured on B200 (profiles/README.md): round 1 (lsa_group): N = 12: G=4 70 us, G=6 of 8 lanes 117 us, G=12 of
 // 16 lanes 94 us per step; N = 6: G=3 of 4 lanes 19.6 us, G=2 20.6 us, G=6 of 8 lanes 23.8 us.  Round 2
 // (lsa_group2, one launch / 4 sub-shard streams): N = 12: G=4 60.2 / 59.0 us, G=6 82.1 / 69.4; N = 6: G=3
 // 18.9 / 19.0, G=6 (one agent per lane, GSM_TEAM_G=6) 22.4 / 16.1 — faster only when several launches overlap
-// (27.7 warps per SM do not fit one wave at 122 registers), so G=3 stays the default.
+// (27.7 warps per SM do not fit one wave at 122 registers); compiled for 5 CTAs per SM (68 registers) G=6 is
+// 17.9 / 16.4 (line-6: 20.9 / 19.0 vs 20.0 / 20.0 with G=3) and is the N = 6 default since.
 
 static bool has_team(const HostParams& hp) {
   if (env_int("GSM_NO_TEAM", 0) != 0 || env_int("GSM_NO_SPEC", 0) != 0 || env_int("GSM_FORCE_P", 0) != 0 ||

@@ -643,13 +643,13 @@ def test_fixed_size_env_variants_and_spaces():
 
 @pytest.mark.parametrize("name,N", [("polygon", 3), ("polygon", 4), ("polygon", 5), ("polygon", 6), ("polygon", 12),
                                     ("line", 3), ("line", 4), ("line", 5), ("line", 6), ("line", 12)])
-@pytest.mark.parametrize("kw", [{}, {"share_reward": True, "max_nbrs": 2}, {"team_g": 2}])
+@pytest.mark.parametrize("kw", [{}, {"share_reward": True, "max_nbrs": 2}, {"team_g": 2}, {"team_g": 3}])
 def test_team_kernel_group_lsa_f64(name, N, kw, monkeypatch):
     """env_team_kernel (G lanes per env, N/G assignment rows per lane): fused 25 steps and single
     steps against the oracle, plus a TIE-HEAVY start (all agents on one point, then agents exactly
     on the slots in reversed order) where only scipy's scan order decides the permutation."""
     kw = dict(kw)
-    if "team_g" in kw:                                      # the non-default lane grouping (N = 6: G=2)
+    if "team_g" in kw:                                      # the non-default lane groupings (N = 6: G = 2, G = 3 of 4 lanes)
         monkeypatch.setenv("GSM_TEAM_G", str(kw.pop("team_g")))
         if N != 6:
             pytest.skip("only N = 6 has a second grouping")
