@@ -328,7 +328,7 @@ int GSM_SFX(launch_lane)(const HostParams& hp, const gsm_step_io& io, int n_step
 // (lsa_group2, one launch / 4 sub-shard streams): N = 12: G=4 60.2 / 59.0 us, G=6 82.1 / 69.4; N = 6: G=3
 // 18.9 / 19.0, G=6 (one agent per lane, GSM_TEAM_G=6) 22.4 / 16.1 — faster only when several launches overlap
 // (27.7 warps per SM do not fit one wave at 122 registers); compiled for 5 CTAs per SM (68 registers) G=6 is
-// 17.9 / 16.4 (line-6: 20.9 / 19.0 vs 20.0 / 20.0 with G=3) and is the N = 6 default since.
+// 17.9 / 16.4 (line-6: 20.9 / 19.0 vs 20.0 / 20.0 with G=3) and is the N = 6 default since.  N = 12 with G=12 of 16 lanes (lsa_group2): 83 / 70 us.
 
 static bool has_team(const HostParams& hp) {
   if (env_int("GSM_NO_TEAM", 0) != 0 || env_int("GSM_NO_SPEC", 0) != 0 || env_int("GSM_FORCE_P", 0) != 0 ||
