@@ -54,8 +54,12 @@ template <typename T> __device__ __forceinline__ void st_zero16(void* p) {
 // the cold auto-reset path must not inflate it.
 // AUTO: compiled-in auto-reset (fused rollouts with gsm_set_auto_reset); the plain variant
 // carries none of that code.
+#ifndef GSM_LANE_BLOCKS        // A/B: resident CTAs per SM the fp32 instances are compiled for
+#define GSM_LANE_BLOCKS 7
+#endif
+template <typename T> struct LaneMinBlocks { static constexpr int value = sizeof(T) == 4 ? GSM_LANE_BLOCKS : 1; };
 template <typename T, bool AUTO>
-__global__ void __launch_bounds__(128, sizeof(T) == 4 ? 7 : 1)
+__global__ void __launch_bounds__(128, LaneMinBlocks<T>::value)
 env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
                 const __grid_constant__ StepStrides ss) {
   extern __shared__ __align__(128) unsigned char sm[];
