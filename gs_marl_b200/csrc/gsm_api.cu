@@ -340,6 +340,8 @@ int copy_out(gsm_env* h, const gsm_step_io& host_io, bool with_rcd) {
       dc.n = 0;
       for (int k = IO_OBS; k < IO_COUNT; k++) {
         if (k == IO_NBR_FEAT || !wanted(k)) continue;
+        // navigation: assign[i] = i on every step — the dense re-synchronisation delivered it, it cannot change
+        if (k == IO_ASSIGN && h->hp.scenario == GSM_SCN_NAVIGATION) continue;
         dc.src[dc.n] = h->d_arena + h->arena_off[k];
         dc.dst[dc.n] = h->h_arena_dev + h->arena_off[k];
         dc.n16[dc.n] = (h->io_bytes[k] + 15) / 16;            // sub-buffers are 256-byte aligned and padded
