@@ -228,8 +228,9 @@ int gsm_host_io(gsm_env* h, gsm_step_io* out);
  * sparse != 0 (default): the pinned arena is mapped and a kernel writes the outputs into it over
  *   PCIe, sending only the nbr_cnt[i] valid rows of nbr_feat per agent (71 % of a dense step's
  *   bytes are nbr_feat, about half of its rows are padding) — the padding rows of the host buffer
- *   already hold zeros and rows that stop being valid are cleared, so the host arrays stay
- *   bit-identical to the device tensors.  sparse == 0: one dense D2H copy per call.
+ *   already hold zeros and rows that stop being valid are cleared — and of nbr_idx only the 16-byte
+ *   pieces that differ from what the host already holds (neighbour sets change slowly), so the host
+ *   arrays stay bit-identical to the device tensors.  sparse == 0: one dense D2H copy per call.
  * A change takes effect with a dense re-synchronisation on the next *_host call. */
 int gsm_set_host_outputs(gsm_env* h, uint32_t out_mask, int32_t sparse);
 int gsm_reset_host(gsm_env* h, uint64_t seed, const uint8_t* mask, int64_t mask_stride,
