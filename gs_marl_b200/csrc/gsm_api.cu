@@ -72,7 +72,8 @@ struct gsm_env {
   // over PCIe and skips the padding rows of nbr_feat / nbr_idx (host rows >= cnt already hold 0 / -1)
   unsigned char* h_arena_dev = nullptr;   // device address of h_arena
   int32_t* d_prev_cnt = nullptr;          // [n_envs*N] neighbour rows the host copy currently holds per agent
-  int32_t* d_prev_idx = nullptr;          // [n_envs*N*K] the nbr_idx the host copy currently holds (K % 4 == 0)
+  unsigned char* d_shadow = nullptr;      // device-side copy of what the host arena holds (same offsets): slowly
+                                          // changing outputs leave as the 16-byte pieces that differ from it
   int host_sparse = 1;                    // GSM_HOST_DENSE=1 / gsm_set_host_outputs(..., sparse = 0): one dense D2H copy instead
   uint32_t host_out_mask = 0xffffffffu;   // bit k: output k (gsm_io index) is delivered to the host by the *_host calls
   int host_resync = 1;                    // next arena copy-out is dense and re-bases d_prev_cnt
@@ -262,7 +263,8 @@ int ensure_host_path(gsm_env* h) {
   GSM_CUDA(h, cudaHostGetDevicePointer((void**)&h->h_arena_dev, h->h_arena, 0));
   GSM_CUDA(h, cudaMalloc((void**)&h->d_prev_cnt, (size_t)h->hp.n_envs * h->hp.N * 4 + 16));
   GSM_CUDA(h, cudaMemset(h->d_prev_cnt, 0, (size_t)h->hp.n_envs * h->hp.N * 4 + 16));
-  if (h->hp.K % 4 == 0) GSM_CUDA(h, cudaMalloc((void**)&h->d_prev_idx, h->io_bytes[IO_NBR_IDX] + 16));
+  GSM_CUDA(h, cudaMalloc((void**)&h->d_shadow, o));
+  GSM_CUDA(h, cudaMemset(h->d_shadow, 0, o));
   if (const char* v = std::getenv("GSM_HOST_DENSE")) h->host_sparse = std::atoi(v) ? 0 : 1;
   h->host_resync = 1;
   GSM_CUDA(h, cudaMalloc((void**)&h->d_mask, (size_t)h->hp.n_envs * h->hp.N + 16));
@@ -281,9 +283,9 @@ bool is_arena_io(const gsm_env* h, const gsm_step_io& io) {
 
 // ---- sparse export kernels (arena host path) ---------------------------------------------------------
 // Of an agent's K neighbour rows only the first cnt are data: that block (cnt * row bytes, contiguous, at
-// the start of the agent's K-row block) is written to the mapped host arena in 8-byte pieces, bytes of rows
-// in [cnt, prev) — valid on the host from an earlier call — are cleared, rows >= max(cnt, prev) already hold
-// zeros there and are not touched.  A warp serves 4 agents per pass.
+// the start of the agent's K-row block) is written to the mapped host arena in 8-byte pieces together with the
+// rows in [cnt, prev) — valid on the host from an earlier call, zeros now — and rows >= max(cnt, prev) already
+// hold zeros there and are not touched.  A warp serves 4 agents per pass.
 // Measured on B200 / PCIe gen5 (profiles/micro/mapped_d2h*.cu, 49152 agents x 8 rows x 24 B): dense DMA of
 // nbr_feat 169 us; this kernel 116-121 us at 38-56 % valid rows (the link carries partial lines as small
 // packets, so time follows the agent count more than the bytes); the same with 16-byte pieces 176 us (kept
@@ -300,32 +302,41 @@ __global__ void export_rows_kernel(const int32_t* __restrict__ cnt, int32_t* __r
       if (a >= rows) continue;
       const int o = (q % ppa) * 8;                            // byte offset inside the agent's block
       const size_t g = (size_t)a * ab + o;
-      if (o < cnt[a] * row_bytes) *(uint2*)(h_feat + g) = *(const uint2*)(feat + g);
-      else if (o < prev[a] * row_bytes) *(uint2*)(h_feat + g) = make_uint2(0u, 0u);
+      // one store path: rows in [cnt, prev) are copied too — the device tensor holds the zeros they must become
+      // (measured 99 us against 115 us with a separate clearing branch, profiles/micro/mapped_d2h2.cu)
+      const int c = cnt[a], pv = prev[a];
+      if (o < (c > pv ? c : pv) * row_bytes) *(uint2*)(h_feat + g) = *(const uint2*)(feat + g);
     }
     __syncwarp();
     if (lane < 4 && a0 + lane < rows) prev[a0 + lane] = cnt[a0 + lane];
   }
 }
 
-// nbr_idx: neighbour sets change slowly (navigation-3: 18 % of the agents per step), so only the 16-byte pieces
-// that differ from what the host already holds are sent (profiles/micro/mapped_idx.cu: 20 % of the rows 16.7 us,
-// the dense 1.57 MB block 35.8 us).  prev = the device-side copy of the host's nbr_idx.
-__global__ void export_idx_kernel(const uint4* __restrict__ idx, uint4* __restrict__ prev, uint4* __restrict__ h_idx,
-                                  unsigned long long n16) {
-  for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n16;
-       q += (unsigned long long)gridDim.x * blockDim.x) {
-    const uint4 c = idx[q], o = prev[q];
-    if (c.x != o.x || c.y != o.y || c.z != o.z || c.w != o.w) { h_idx[q] = c; prev[q] = c; }
-  }
-}
-
-struct DenseCopies { const unsigned char* src[8]; unsigned char* dst[8]; unsigned long long n16[8]; int n; };
+// The other outputs leave in 16-byte pieces.  Slowly changing ones — nbr_idx (navigation-3: 18 % of the agents
+// per step), nbr_cnt, adj, cost (mostly 0), done, assign — are compared with a device-side SHADOW of what the
+// host already holds and only the pieces that differ are sent (profiles/micro/mapped_idx.cu: 20 % of the
+// nbr_idx rows 16.7 us, the dense 1.57 MB block 35.8 us); obs and reward change everywhere and go out dense.
+struct DenseCopies {
+  const unsigned char* src[8]; unsigned char* dst[8]; unsigned char* shadow[8];   // shadow NULL: send every piece
+  unsigned long long n16[8];
+  int n;
+};
 __global__ void export_dense_kernel(const __grid_constant__ DenseCopies c) {
-  for (int k = 0; k < c.n; k++)
+  for (int k = 0; k < c.n; k++) {
+    const uint4* src = (const uint4*)c.src[k];
+    uint4* dst = (uint4*)c.dst[k];
+    uint4* sh = (uint4*)c.shadow[k];
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < c.n16[k];
-         i += (unsigned long long)gridDim.x * blockDim.x)
-      ((uint4*)c.dst[k])[i] = ((const uint4*)c.src[k])[i];
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+      const uint4 v = src[i];
+      if (sh) {
+        const uint4 o = sh[i];
+        if (v.x == o.x && v.y == o.y && v.z == o.z && v.w == o.w) continue;
+        sh[i] = v;
+      }
+      dst[i] = v;
+    }
+  }
 }
 
 // D2H of the outputs of a host-path call.
@@ -348,26 +359,17 @@ int copy_out(gsm_env* h, const gsm_step_io& host_io, bool with_rcd) {
                                         cudaMemcpyDeviceToHost, h->stream));
       }
       GSM_CUDA(h, cudaMemcpyAsync(h->d_prev_cnt, h->d_io.nbr_cnt, (size_t)rows * 4, cudaMemcpyDeviceToDevice, h->stream));
-      if (h->d_prev_idx)
-        GSM_CUDA(h, cudaMemcpyAsync(h->d_prev_idx, h->d_io.nbr_idx, h->io_bytes[IO_NBR_IDX], cudaMemcpyDeviceToDevice, h->stream));
+      GSM_CUDA(h, cudaMemcpyAsync(h->d_shadow + h->arena_out_begin, h->d_arena + h->arena_out_begin,
+                                  h->arena_total - h->arena_out_begin, cudaMemcpyDeviceToDevice, h->stream));
       h->host_resync = 0;
     } else {
       DenseCopies dc;
       dc.n = 0;
       for (int k = IO_OBS; k < IO_COUNT; k++) {
         if (k == IO_NBR_FEAT || !wanted(k)) continue;
-        // navigation: assign[i] = i on every step — the dense re-synchronisation delivered it, it cannot change
-        if (k == IO_ASSIGN && h->hp.scenario == GSM_SCN_NAVIGATION) continue;
-        if (k == IO_NBR_IDX && h->d_prev_idx) {              // changed 16-byte pieces only
-          export_idx_kernel<<<148, 256, 0, h->stream>>>((const uint4*)h->d_io.nbr_idx, (uint4*)h->d_prev_idx,
-                                                        (uint4*)(h->h_arena_dev + h->arena_off[IO_NBR_IDX]),
-                                                        (unsigned long long)(h->io_bytes[IO_NBR_IDX] / 16));
-          GSM_CUDA(h, cudaGetLastError());
-          h->launches += 1;
-          continue;
-        }
         dc.src[dc.n] = h->d_arena + h->arena_off[k];
         dc.dst[dc.n] = h->h_arena_dev + h->arena_off[k];
+        dc.shadow[dc.n] = (k == IO_OBS || k == IO_REWARD) ? nullptr : h->d_shadow + h->arena_off[k];
         dc.n16[dc.n] = (h->io_bytes[k] + 15) / 16;            // sub-buffers are 256-byte aligned and padded
         dc.n++;
       }
@@ -526,7 +528,7 @@ int gsm_destroy(gsm_env* h) {
   if (h->d_arena) cudaFree(h->d_arena);
   if (h->h_arena) cudaFreeHost(h->h_arena);
   if (h->d_prev_cnt) cudaFree(h->d_prev_cnt);
-  if (h->d_prev_idx) cudaFree(h->d_prev_idx);
+  if (h->d_shadow) cudaFree(h->d_shadow);
   if (h->d_mask) cudaFree(h->d_mask);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;

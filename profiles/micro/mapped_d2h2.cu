@@ -7,6 +7,29 @@
 #include <cuda_runtime.h>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
+__global__ void export_rows_rnd(const int* __restrict__ cnt, int* __restrict__ prev, const unsigned char* __restrict__ feat,
+                                unsigned char* __restrict__ h_feat, long long rows, int row_bytes, int K, int RND) {
+  // 8-byte pieces; the valid prefix is rounded UP to a multiple of RND bytes (the extra bytes are the zeros the
+  // dense tensor holds there anyway): whole 32- / 64- / 128-byte lines instead of partial ones
+  const int lane = threadIdx.x & 31;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int ab = K * row_bytes, ppa = ab / 8;
+  for (long long a0 = w * 4; a0 < rows; a0 += nw * 4) {
+    for (int q = lane; q < 4 * ppa; q += 32) {
+      const long long a = a0 + q / ppa;
+      if (a >= rows) continue;
+      const int o = (q % ppa) * 8;
+      const size_t g = (size_t)a * ab + o;
+      int vb = cnt[a] * row_bytes, pb = prev[a] * row_bytes;
+      vb = vb > pb ? vb : pb;
+      // round the end up to RND relative to the ABSOLUTE address (line boundaries)
+      const size_t end = ((size_t)a * ab + vb + RND - 1) / RND * RND;
+      if (g < end && o < ab) *(uint2*)(h_feat + g) = *(const uint2*)(feat + g);
+    }
+    __syncwarp();
+    if (lane < 4 && a0 + lane < rows) prev[a0 + lane] = cnt[a0 + lane];
+  }
+}
 template <int PB>
 __global__ void export_rows(const int* __restrict__ cnt, int* __restrict__ prev, const unsigned char* __restrict__ feat,
                             unsigned char* __restrict__ h_feat, long long rows, int row_bytes, int K, int APW) {
@@ -68,6 +91,8 @@ int main() {
   for (int g : {148, 296, 1184})
     timeit("rows PB=16 APW=8 grid " + std::to_string(g), valid * 24, [&](int i) { export_rows<16><<<g, 256, 0, st>>>(i & 1 ? d_cnt2 : d_cnt, d_prev, d_src, d_map, rows, 24, K, 8); });
   timeit("rows PB=16 APW=4 grid 296", valid * 24, [&](int i) { export_rows<16><<<296, 256, 0, st>>>(i & 1 ? d_cnt2 : d_cnt, d_prev, d_src, d_map, rows, 24, K, 4); });
+  for (int rnd : {8, 32, 64, 128})
+    timeit("rows rounded up to " + std::to_string(rnd) + " B lines", valid * 24, [&](int i) { export_rows_rnd<<<296, 256, 0, st>>>(i & 1 ? d_cnt2 : d_cnt, d_prev, d_src, d_map, rows, 24, K, rnd); });
   for (int g : {74, 148, 592})
     timeit("dense small 3.8 MB kernel grid " + std::to_string(g), small, [&](int) { copy_dense<<<g, 256, 0, st>>>((const uint4*)d_small, (uint4*)(d_map + bytes), small / 16); });
   timeit("dense small 3.8 MB cudaMemcpyAsync", small, [&](int) { CK(cudaMemcpyAsync(h_map + bytes, d_small, small, cudaMemcpyDeviceToHost, st)); });
