@@ -30,6 +30,23 @@ __global__ void export_rows_rnd(const int* __restrict__ cnt, int* __restrict__ p
     if (lane < 4 && a0 + lane < rows) prev[a0 + lane] = cnt[a0 + lane];
   }
 }
+// LPA lanes per agent, each lane walks its agent's valid prefix in 8-byte pieces with stride LPA
+template <int LPA>
+__global__ void export_rows_lpa(const int* __restrict__ cnt, int* __restrict__ prev, const unsigned char* __restrict__ feat,
+                                unsigned char* __restrict__ h_feat, long long rows, int row_bytes, int K) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+  const int ab = K * row_bytes;
+  for (long long a = t / LPA; a < rows; a += nt / LPA) {
+    const int sub = (int)(t % LPA);
+    const int c = cnt[a], pv = prev[a];
+    const int vb = (c > pv ? c : pv) * row_bytes;
+    for (int o = sub * 8; o < vb; o += LPA * 8) {
+      const size_t g = (size_t)a * ab + o;
+      *(uint2*)(h_feat + g) = *(const uint2*)(feat + g);
+    }
+    if (sub == 0) prev[a] = c;
+  }
+}
 template <int PB>
 __global__ void export_rows(const int* __restrict__ cnt, int* __restrict__ prev, const unsigned char* __restrict__ feat,
                             unsigned char* __restrict__ h_feat, long long rows, int row_bytes, int K, int APW) {
@@ -91,6 +108,12 @@ int main() {
   for (int g : {148, 296, 1184})
     timeit("rows PB=16 APW=8 grid " + std::to_string(g), valid * 24, [&](int i) { export_rows<16><<<g, 256, 0, st>>>(i & 1 ? d_cnt2 : d_cnt, d_prev, d_src, d_map, rows, 24, K, 8); });
   timeit("rows PB=16 APW=4 grid 296", valid * 24, [&](int i) { export_rows<16><<<296, 256, 0, st>>>(i & 1 ? d_cnt2 : d_cnt, d_prev, d_src, d_map, rows, 24, K, 4); });
+  timeit("rows LPA=1", valid * 24, [&](int i) { export_rows_lpa<1><<<296, 256, 0, st>>>(i & 1 ? d_cnt2 : d_cnt, d_prev, d_src, d_map, rows, 24, K); });
+  timeit("rows LPA=2", valid * 24, [&](int i) { export_rows_lpa<2><<<296, 256, 0, st>>>(i & 1 ? d_cnt2 : d_cnt, d_prev, d_src, d_map, rows, 24, K); });
+  timeit("rows LPA=4", valid * 24, [&](int i) { export_rows_lpa<4><<<296, 256, 0, st>>>(i & 1 ? d_cnt2 : d_cnt, d_prev, d_src, d_map, rows, 24, K); });
+  timeit("rows LPA=8", valid * 24, [&](int i) { export_rows_lpa<8><<<296, 256, 0, st>>>(i & 1 ? d_cnt2 : d_cnt, d_prev, d_src, d_map, rows, 24, K); });
+  timeit("rows LPA=8 grid 1184", valid * 24, [&](int i) { export_rows_lpa<8><<<1184, 256, 0, st>>>(i & 1 ? d_cnt2 : d_cnt, d_prev, d_src, d_map, rows, 24, K); });
+  timeit("rows LPA=4 grid 74", valid * 24, [&](int i) { export_rows_lpa<4><<<74, 256, 0, st>>>(i & 1 ? d_cnt2 : d_cnt, d_prev, d_src, d_map, rows, 24, K); });
   for (int rnd : {8, 32, 64, 128})
     timeit("rows rounded up to " + std::to_string(rnd) + " B lines", valid * 24, [&](int i) { export_rows_rnd<<<296, 256, 0, st>>>(i & 1 ? d_cnt2 : d_cnt, d_prev, d_src, d_map, rows, 24, K, rnd); });
   for (int g : {74, 148, 592})
