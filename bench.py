@@ -510,9 +510,10 @@ def run_gpu(args):
             "e2e": {"value": agents * Ke * world / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "d2h_bytes_per_step_dense": d2h_dense,
                     "steps": Ke,
-                    "api": "GraphVecEnv.step -> gsm_step_host (mapped pinned arena; 1 H2D copy + the step kernel + 2 "
-                           "export kernels that write every output into the host arrays over PCIe, sending only the "
-                           "nbr_cnt valid rows of nbr_feat; all nine host arrays bit-identical to the device tensors)",
+                    "api": "GraphVecEnv.step -> gsm_step_host (mapped pinned arena; 1 H2D copy + the step kernel + one "
+                           "export kernel that writes the outputs into the host arrays over PCIe: the nbr_cnt valid rows "
+                           "of nbr_feat, obs / reward in full, the 16-byte pieces of the other outputs that changed; all "
+                           "nine host arrays bit-identical to the device tensors)",
                     "host_affinity": numa,
                     "bound": "PCIe D2H of the step's outputs",
                     "d2h_gbs_achieved": d2h * Ke / e2e_s / 1e9,

@@ -290,11 +290,16 @@ bool is_arena_io(const gsm_env* h, const gsm_step_io& io) {
 // nbr_feat 169 us; this kernel 116-121 us at 38-56 % valid rows (the link carries partial lines as small
 // packets, so time follows the agent count more than the bytes); the same with 16-byte pieces 176 us (kept
 // out); nbr_idx with 4-byte scattered writes cost +100 us per step, so it leaves dense with the small outputs.
-__global__ void export_rows_kernel(const int32_t* __restrict__ cnt, int32_t* __restrict__ prev,
-                                   const unsigned char* __restrict__ feat, unsigned char* __restrict__ h_feat,
-                                   int64_t rows, int row_bytes, int K) {
+struct RowsExport { const int32_t* cnt; int32_t* prev; const unsigned char* feat; unsigned char* h_feat; int64_t rows; int row_bytes, K; };
+__device__ __forceinline__ void export_rows(const RowsExport& r, int block, int n_blocks) {
+  const int32_t* __restrict__ cnt = r.cnt;
+  int32_t* __restrict__ prev = r.prev;
+  const unsigned char* __restrict__ feat = r.feat;
+  unsigned char* __restrict__ h_feat = r.h_feat;
+  const int64_t rows = r.rows;
+  const int row_bytes = r.row_bytes, K = r.K;
   const int lane = threadIdx.x & 31;
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t w = ((int64_t)block * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)n_blocks * blockDim.x) >> 5;
   const int ab = K * row_bytes, ppa = ab / 8;                // bytes / 8-byte pieces per agent
   for (int64_t a0 = w * 4; a0 < rows; a0 += nw * 4) {
     for (int q = lane; q < 4 * ppa; q += 32) {
@@ -321,13 +326,13 @@ struct DenseCopies {
   unsigned long long n16[8];
   int n;
 };
-__global__ void export_dense_kernel(const __grid_constant__ DenseCopies c) {
+__device__ __forceinline__ void export_dense(const DenseCopies& c, int block, int n_blocks) {
   for (int k = 0; k < c.n; k++) {
     const uint4* src = (const uint4*)c.src[k];
     uint4* dst = (uint4*)c.dst[k];
     uint4* sh = (uint4*)c.shadow[k];
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < c.n16[k];
-         i += (unsigned long long)gridDim.x * blockDim.x) {
+    for (unsigned long long i = (unsigned long long)block * blockDim.x + threadIdx.x; i < c.n16[k];
+         i += (unsigned long long)n_blocks * blockDim.x) {
       const uint4 v = src[i];
       if (sh) {
         const uint4 o = sh[i];
@@ -337,6 +342,13 @@ __global__ void export_dense_kernel(const __grid_constant__ DenseCopies c) {
       dst[i] = v;
     }
   }
+}
+
+// ONE launch: blocks [0, rows_blocks) export the valid rows of nbr_feat, the others the 16-byte pieces
+// (a second launch cost ~5 us on the critical path of a 200 us step).
+__global__ void export_kernel(const __grid_constant__ RowsExport r, const __grid_constant__ DenseCopies c, const int rows_blocks) {
+  if ((int)blockIdx.x < rows_blocks) export_rows(r, (int)blockIdx.x, rows_blocks);
+  else export_dense(c, (int)blockIdx.x - rows_blocks, (int)gridDim.x - rows_blocks);
 }
 
 // D2H of the outputs of a host-path call.
@@ -373,19 +385,13 @@ int copy_out(gsm_env* h, const gsm_step_io& host_io, bool with_rcd) {
         dc.n16[dc.n] = (h->io_bytes[k] + 15) / 16;            // sub-buffers are 256-byte aligned and padded
         dc.n++;
       }
-      if (wanted(IO_NBR_FEAT)) {
-        export_rows_kernel<<<296, 256, 0, h->stream>>>(h->d_io.nbr_cnt, h->d_prev_cnt, (const unsigned char*)h->d_io.nbr_feat,
-                                                       h->h_arena_dev + h->arena_off[IO_NBR_FEAT], rows, GSM_NBR_FEAT_DIM * h->rb, h->hp.K);
-        GSM_CUDA(h, cudaGetLastError());
-        h->launches += 1;
-      }
-      static const int dense_memcpy = std::getenv("GSM_HOST_DENSE_MEMCPY") ? std::atoi(std::getenv("GSM_HOST_DENSE_MEMCPY")) : 0;
-      if (dc.n && dense_memcpy) {                              // A/B: the copy engine instead of the kernel
-        for (int k = 0; k < dc.n; k++)
-          GSM_CUDA(h, cudaMemcpyAsync(h->h_arena + (dc.dst[k] - h->h_arena_dev), dc.src[k], dc.n16[k] * 16,
-                                      cudaMemcpyDeviceToHost, h->stream));
-      } else if (dc.n) {
-        export_dense_kernel<<<148, 256, 0, h->stream>>>(dc);
+      RowsExport re;
+      re.cnt = h->d_io.nbr_cnt; re.prev = h->d_prev_cnt; re.feat = (const unsigned char*)h->d_io.nbr_feat;
+      re.h_feat = h->h_arena_dev + h->arena_off[IO_NBR_FEAT]; re.rows = rows; re.row_bytes = GSM_NBR_FEAT_DIM * h->rb;
+      re.K = h->hp.K;
+      const int rows_blocks = wanted(IO_NBR_FEAT) ? 296 : 0, dense_blocks = dc.n ? 148 : 0;
+      if (rows_blocks + dense_blocks) {
+        export_kernel<<<rows_blocks + dense_blocks, 256, 0, h->stream>>>(re, dc, rows_blocks);
         GSM_CUDA(h, cudaGetLastError());
         h->launches += 1;
       }

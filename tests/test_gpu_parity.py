@@ -434,7 +434,7 @@ def test_rollout_graph_equals_sequential_steps_and_host_path():
         obs, graph, rew, cost, done, infos = vec.step(acts[t])
     for k in OUT_KEYS:
         assert (vec.buf[k] == _np(seq[-1])[k].view(vec.buf[k].dtype)).all(), k
-    assert vec.kernel_launches == T + 2 * (T - 1)          # T steps; every step after the dense first one: 2 export kernels
+    assert vec.kernel_launches == T + (T - 1)              # T steps; every step after the dense first one: 1 export kernel
     env.close(); vec.close()
 
 
