@@ -509,6 +509,9 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": agents * Ke * world / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "d2h_bytes_per_step_dense": d2h_dense,
+                    "d2h_bytes_note": "d2h_bytes_per_step = the small outputs in full + the nbr_cnt valid rows of nbr_feat "
+                                      "(last step's counts): an UPPER bound, the slowly changing small outputs cross as "
+                                      "changed 16-byte pieces only; d2h_bytes_per_step_dense = the nine host arrays",
                     "steps": Ke,
                     "api": "GraphVecEnv.step -> gsm_step_host (mapped pinned arena; 1 H2D copy + the step kernel + one "
                            "export kernel that writes the outputs into the host arrays over PCIe: the nbr_cnt valid rows "
