@@ -178,6 +178,46 @@ __host__ __device__ constexpr TeamLsaSmem team_lsa_smem(int rb, int N) {
   return t;
 }
 
+// Minimum / maximum over the GP lanes of a group: log2(GP) xor-shuffle + compare stages.  The alternative — ONE
+// redux.sync over the group's lane mask (order-preserving integer key for the float) — is 2.3x SLOWER end to end
+// (polygon-12 137 vs 60 us per step, -DGSM_TEAM_REDUX=1): a redux.sync over a sub-warp mask is executed once per
+// distinct mask, i.e. 8 times per warp here.
+#ifndef GSM_TEAM_REDUX
+#define GSM_TEAM_REDUX 0
+#endif
+template <int GP>
+__device__ __forceinline__ float group_min(float v, unsigned gmask) {
+#if GSM_TEAM_REDUX
+  if (GP > 1) {
+    const unsigned b = __float_as_uint(v);
+    const unsigned key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    const unsigned r = __reduce_min_sync(gmask, key);
+    return __uint_as_float((r & 0x80000000u) ? (r & 0x7fffffffu) : ~r);
+  }
+  return v;
+#else
+#pragma unroll
+  for (int m = GP / 2; m >= 1; m >>= 1) { const float o = __shfl_xor_sync(0xffffffffu, v, m); v = o < v ? o : v; }
+  return v;
+#endif
+}
+template <int GP>
+__device__ __forceinline__ double group_min(double v, unsigned) {
+#pragma unroll
+  for (int m = GP / 2; m >= 1; m >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, v, m); v = o < v ? o : v; }
+  return v;
+}
+template <int GP>
+__device__ __forceinline__ int group_max(int v, unsigned gmask) {
+#if GSM_TEAM_REDUX
+  return GP > 1 ? __reduce_max_sync(gmask, v) : v;
+#else
+#pragma unroll
+  for (int m = GP / 2; m >= 1; m >>= 1) { const int o = __shfl_xor_sync(0xffffffffu, v, m); v = o > v ? o : v; }
+  return v;
+#endif
+}
+
 // One shortest-augmenting-path step for row `cur` of every ACTIVE group, in lockstep: Dijkstra search from
 // the current duals and matching, dual update, augmentation.  v[] (my column duals) lives in registers, the
 // rest of the solver state in the env's shared-memory block.  Inactive groups idle.
@@ -195,6 +235,7 @@ __device__ __forceinline__ void lsa_augment(const T* __restrict__ C, uint32_t* _
   int* const spath = (int*)(ws + L.path);
   const int col0 = (g < G ? g : 0) * A;                   // my first column / row
   const T* Cg = C + col0;
+  const unsigned gmask = low_mask(GP) << ((threadIdx.x & 31) / GP * GP);   // the lanes of my group
   T spc[A];
   int path[A], pos[A], keyp[A];
   bool asg[A];                                            // my column is assigned (row4col != -1)
@@ -225,11 +266,7 @@ __device__ __forceinline__ void lsa_augment(const T* __restrict__ C, uint32_t* _
       const T cand = in_a ? spc[a] : INF;
       lo = cand < lo ? cand : lo;
     }
-#pragma unroll
-    for (int m = GP / 2; m >= 1; m >>= 1) {
-      const T o = __shfl_xor_sync(FULL, lo, m);
-      lo = o < lo ? o : lo;
-    }
+    lo = group_min<GP>(lo, gmask);
     // tie rule: an unassigned minimum with the largest position wins, else the minimum with the smallest
     // position; positions are unique, the column index rides in the low bits of the key
     int best = -1;
@@ -238,11 +275,7 @@ __device__ __forceinline__ void lsa_augment(const T* __restrict__ C, uint32_t* _
       const int packed = (((inr >> a) & 1u) && spc[a] == lo) ? keyp[a] : -1;
       best = packed > best ? packed : best;
     }
-#pragma unroll
-    for (int m = GP / 2; m >= 1; m >>= 1) {
-      const int o = __shfl_xor_sync(FULL, best, m);
-      best = o > best ? o : best;
-    }
+    best = group_max<GP>(best, gmask);
     const int key = best >> 6, j = best < 0 ? 0 : (best & 63);
     const int selpos = key >= 64 ? key - 64 : 31 - key;
     const int r4c_j = sr4c[j];
