@@ -57,9 +57,20 @@ template <typename T> __device__ __forceinline__ void st_zero16(void* p) {
 #ifndef GSM_LANE_BLOCKS        // A/B: resident CTAs per SM the fp32 instances are compiled for
 #define GSM_LANE_BLOCKS 7
 #endif
-template <typename T> struct LaneMinBlocks { static constexpr int value = sizeof(T) == 4 ? GSM_LANE_BLOCKS : 1; };
-template <typename T, bool AUTO>
-__global__ void __launch_bounds__(128, LaneMinBlocks<T>::value)
+#ifndef GSM_LANE_BLOCKS_CARRY  // ... of the CARRY instances (large teams; 6 -> 80 registers)
+#define GSM_LANE_BLOCKS_CARRY 6
+#endif
+template <typename T, bool CARRY> struct LaneMinBlocks {
+  static constexpr int value = sizeof(T) != 4 ? 1 : (CARRY ? GSM_LANE_BLOCKS_CARRY : GSM_LANE_BLOCKS);
+};
+// CARRY (fp32, chosen by the launcher for N >= GSM_LANE_CARRY_MIN_N = 48): the graph phase of step s also sums the
+// contact force of step s+1 from the same table and rounded distances, so the collider sweep runs only on the
+// first step of a launch and after a re-draw.  Round 1 rejected it for every N under the 72-register cap
+// (profiles/rejected/lane_contact_force_carry.diff); as its own instance with 80 registers it pays where the
+// sweeps dominate: nav-48 51.8 -> 49.6 us/step, nav-96 131.9 -> 119.2 (4 streams; one launch 57.3 -> 56.4,
+// 143.2 -> 129.5), and costs small teams (nav-24 one launch 26.1 -> 33.3, nav-12 24.9 -> 32.8): not used there.
+template <typename T, bool AUTO, bool CARRY>
+__global__ void __launch_bounds__(128, LaneMinBlocks<T, CARRY>::value)
 env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
                 const __grid_constant__ StepStrides ss) {
   extern __shared__ __align__(128) unsigned char sm[];
@@ -128,6 +139,15 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   // every contact distance below the sensing radius: a colliding pair is a neighbour candidate
   // anyway, so the candidate sweep needs one squared-distance test per pair instead of two
   const bool col_in_nb = ((T)2 * max_size) * (T)1.0001 < p.Rs;
+  // fp32, and every pair that can contribute to the contact force (dist <= size_i + size_j + cut)
+  // lies inside the sensing radius: the graph phase of step s already takes the rounded distance of
+  // exactly those pairs on the table that step s+1's forces are computed from, so it also sums the
+  // contact force of step s+1 ("carry") and the collider sweep (nc of the E + nc pair tests per
+  // step) runs only on the first step of a launch and after a re-draw.  Summation order changes
+  // (SPEC §9 production deviation 4); fp64 keeps the exact two-sweep sequence.
+  const bool carry_ok = CARRY && Prec<T>::kCut && ((T)2 * max_size + (T)kFarCut * p.km) * (T)1.0001 < p.Rs;
+  T cfx = 0, cfy = 0;
+  bool have_carry = false;
 
   const int ii = active ? i : 0;
   T px = ent[ii].x, py = ent[ii].y, vx = vel[2 * ii], vy = vel[2 * ii + 1];
@@ -169,7 +189,8 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         if (a >= 0 && a < p.n_actions) { ux = p.discrete_u[a][0]; uy = p.discrete_u[a][1]; }
       } else { ux = ((const T*)c_act)[0]; uy = ((const T*)c_act)[1]; }
       fx = accel_i * ux; fy = accel_i * uy;
-      if (coll_i) {
+      if (coll_i && have_carry) { fx = fx + cfx; fy = fy + cfy; }
+      else if (coll_i) {
         // per 32-collider block: a branch-free, sqrt-free sweep (unrolled groups of 8 over the padded
         // list) marks the pairs that can be in contact; only those, in ascending order like SPEC §3,
         // go through sqrt / softplus.  fp64 marks every pair.
@@ -253,6 +274,8 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     // ---- SPEC §6-7: neighbour graph on the new table --------------------------------------------
     int cnt = 0, ncol = 0;
     T r = 0;
+    const bool want_carry = carry_ok && coll_i && step + 1 < n_steps;
+    cfx = 0; cfy = 0;
     if (active) {
       // per 32-entity block: a branch-free, sqrt-free sweep (unrolled groups of 8 over the padded
       // table) marks candidates on the squared distance (a few ulp inclusive); the set bits, in
@@ -288,6 +311,14 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
           const T dx = q.x - px, dy = q.y - py;
           const T dist = A::sqrt(dx * dx + dy * dy);
           if (dist < size_i + q.size && ((cmask >> k) & 1u)) ncol++;
+          if (want_carry && (q.flag & 1)) {            // SPEC §3 term of the NEXT step (dx is other - self here)
+            const T x = A::div_const(-(dist - (size_i + q.size)), p.km, p.km_inv);
+            if (!(x < (T)(-kFarCut))) {
+              const T pen = softplus(x) * p.km;
+              cfx = cfx - A::div(p.cf * dx, dist) * pen;
+              cfy = cfy - A::div(p.cf * dy, dist) * pen;
+            }
+          }
           if (dist < p.Rs || e == goal_e) {
             word |= 1u << k;
             if (cnt < K) {
@@ -340,6 +371,9 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       }
       if (multi) __syncthreads(); else __syncwarp();
       if (rs) { gxl = ent[N + i].x; gyl = ent[N + i].y; t_now = 0; ep += 1; }
+      have_carry = want_carry && !rs;                  // a re-drawn table invalidates the carried force
+    } else {
+      have_carry = want_carry;
     }
     c_act += ss.actions; c_idx += ss.nbr_idx; c_feat += ss.nbr_feat; c_obs += ss.obs;
     c_cnt += ss.nbr_cnt; c_adj += ss.adj; c_rew += ss.reward; c_cost += ss.cost;

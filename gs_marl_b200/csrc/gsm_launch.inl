@@ -302,7 +302,9 @@ int GSM_SFX(launch_lane)(const HostParams& hp, const gsm_step_io& io, int n_step
   const LaneGeom g = lane_geom(hp.N);
   const size_t smem = lane_smem((int)sizeof(LaneEnt<GSM_REAL>), (int)sizeof(GSM_REAL), hp.N, hp.N + hp.L,
                                 g.envs_per_cta);
-  auto k = hp.auto_reset ? env_lane_kernel<GSM_REAL, true> : env_lane_kernel<GSM_REAL, false>;
+  const bool carry = sizeof(GSM_REAL) == 4 && hp.N >= env_int("GSM_LANE_CARRY_MIN_N", 48);
+  auto k = carry ? (hp.auto_reset ? env_lane_kernel<GSM_REAL, true, true> : env_lane_kernel<GSM_REAL, false, true>)
+                 : (hp.auto_reset ? env_lane_kernel<GSM_REAL, true, false> : env_lane_kernel<GSM_REAL, false, false>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
