@@ -211,13 +211,16 @@ static int launch_wide_one(const HostParams& hp, const KParams<GSM_REAL>& kp, in
   const int64_t grid = (kp.n_envs + EPW * WPC - 1) / (EPW * WPC);
   const size_t smem = wide_smem_bytes((int)sizeof(T), N, E, kp.K, EPW);
   auto k = observe ? env_wide_kernel<T, N, L, 1, KT> : (kp.auto_reset ? env_wide_kernel<T, N, L, 2, KT> : env_wide_kernel<T, N, L, 0, KT>);
-  static bool attr_done[3] = {false, false, false};      // per instance (this function is one per (T, N, L))
+  // function attributes are per device: one bit per (instance, device), set on first use there
+  static unsigned long long attr_done[3] = {0, 0, 0};    // per instance (this function is one per (T, N, L, K))
   const int which = observe ? 1 : (kp.auto_reset ? 2 : 0);
-  if (!attr_done[which]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !((attr_done[which] >> dev) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem > 48 * 1024 ? (int)smem : 48 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
-    attr_done[which] = true;
+    if (dev >= 0 && dev < 64) attr_done[which] |= 1ull << dev;
   }
   k<<<(unsigned)grid, kWideThreads, smem, st>>>(kp, observe ? 1 : n_steps, ss, wc, wide_smem_layout((int)sizeof(T), N, E, kp.K, EPW));
   return (int)cudaGetLastError();
