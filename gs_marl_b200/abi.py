@@ -113,7 +113,6 @@ SYMBOLS = {
     "gsm_set_state_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_get_state_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_kernel_launches": (C.c_int64, [_H]),
-    "gsm_debug_team_stats": (C.c_int, [C.c_void_p]),
     "gsm_lsa": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int,
                           C.c_void_p]),
     "gsm_policy_act": (C.c_int, [C.POINTER(GsmPolicyWeights), C.POINTER(GsmPolicyIO), C.c_int, C.c_void_p]),

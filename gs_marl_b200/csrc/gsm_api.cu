@@ -821,15 +821,6 @@ int gsm_collect(gsm_env* h, const gsm_policy_weights* w, int32_t n_steps, const 
 
 int64_t gsm_kernel_launches(const gsm_env* h) { return h ? h->launches : 0; }
 
-int gsm_debug_team_stats(uint64_t* out8) {
-  if (!out8) return GSM_ERR_INVALID_ARG;
-  cudaDeviceSynchronize();
-  unsigned long long t[8];
-  if (gsm::team_stats_f32(t) != 0) return GSM_ERR_CUDA;
-  for (int k = 0; k < 8; k++) out8[k] = t[k];
-  return GSM_OK;
-}
-
 int gsm_lsa(const void* cost, int32_t* col4row, int64_t n_problems, int32_t n, int32_t dtype,
             int device, void* stream) {
   if (!cost || !col4row || n_problems < 0 || n < 1 || n > GSM_MAX_LSA_N)

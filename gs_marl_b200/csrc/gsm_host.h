@@ -78,8 +78,6 @@ int launch_team_f32(const HostParams& hp, const gsm_step_io& io, int n_steps,
                     const RolloutStrides& rs, cudaStream_t st);
 int launch_team_f64(const HostParams& hp, const gsm_step_io& io, int n_steps,
                     const RolloutStrides& rs, cudaStream_t st);
-int team_stats_f32(unsigned long long* out8);
-int team_stats_f64(unsigned long long* out8);
 int launch_reset_f32(const HostParams& hp, uint64_t seed, const uint8_t* mask, int64_t mask_stride,
                      cudaStream_t st);
 int launch_reset_f64(const HostParams& hp, uint64_t seed, const uint8_t* mask, int64_t mask_stride,

@@ -143,17 +143,6 @@ __device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int ba
   }
 }
 
-#ifndef GSM_TEAM_STATS         // diagnostics build: count what the warm start does (gsm_team_stats_f32 reads them)
-#define GSM_TEAM_STATS 0
-#endif
-#if GSM_TEAM_STATS
-// 0 solves, 1 warm attempts, 2 certified, 3 cold solves, 4 free rows, 5 warp-level augment rounds, 6 warp-level cold runs, 7 incomplete
-__device__ unsigned long long g_team_stats[8];
-#define TEAM_STAT(k, n) atomicAdd(&g_team_stats[k], (unsigned long long)(n))
-#else
-#define TEAM_STAT(k, n) ((void)0)
-#endif
-
 // ---- round 2: the same solver with a leaner lockstep iteration -------------------------------------------
 // lsa_group spends 165 instructions per Dijkstra iteration (profiles/ncu_r2_team_polygon12_lines.txt): select
 // chains that index per-lane register arrays with a run-time index (u[il], r4c[jl], path[jl]: 16), the relax
@@ -358,171 +347,11 @@ __device__ __forceinline__ void lsa_group2(const T* __restrict__ C, uint32_t* __
   for (int a = 0; a < A; a++) c4r_out[a] = live ? ((const int*)(ws + L.c4r))[col0 + a] : -1;
 }
 
-// ---- warm start (fp32 production mode) ----------------------------------------------------------------------
-// Between two env steps the agents move a few hundredths: most of the previous step's matching and duals are
-// still right.  The solver state (column duals in registers, matching in shared memory) is kept across the
-// steps of a fused launch, and a step does
-//   1. two Bellman-Ford rounds that re-centre the column duals under the OLD matching
-//        v_k <- min(v_k, min_r v_pi(r) + C[r][k] - C[r][pi(r)])     (dual feasibility where the matching still fits),
-//   2. u_r = min_k C[r][k] - v_k; a row keeps its column iff its matched edge attains that minimum, the others
-//      become free (CPU simulation on oracle trajectories, polygon-12: 2.0 free rows per env per step, 4.8 in the
-//      worst of 8 envs; without step 1: 4.2 / 6.5; a cold solve: 12),
-//   3. one lsa_augment per free row (any order: the result is an optimal matching with optimal duals),
-//   4. a CERTIFICATE that the optimum is unique by a margin, so that it is the permutation scipy returns: the
-//      non-matching edges with slack <= tol, read as a graph on rows (r -> row matched to that column), must be
-//      acyclic — every other perfect matching then contains an edge with slack > tol in each of its alternating
-//      cycles and costs > tol more.  tol = 16 N eps * (largest cost) covers the rounding of the slacks.  When the
-//      certificate fails (ties, near-ties: 1 % of the env-steps at this tol) the group runs the cold solve.
-// Prototype with the same steps against scipy, tie-heavy inputs included: scratch-free copy in profiles/warm_proto.py.
-template <typename T, int N, int G, int GP>
-__device__ __forceinline__ void lsa_warm(const T* __restrict__ C, uint32_t* __restrict__ ws, int g, int base,
-                                         bool grp_live, T (&v)[N / G], bool& valid, T cmax, int (&c4r_out)[N / G]) {
-  constexpr int A = N / G;
-  constexpr unsigned FULL = 0xffffffffu;
-  constexpr TeamLsaSmem L = team_lsa_smem((int)sizeof(T), N);
-  const bool live = grp_live && g < G;
-  const T INF = r_inf<T>();
-  T* const su = (T*)(ws + L.u);
-  T* const sw = (T*)(ws + L.spc);                         // scratch [N] (the path costs are dead between solves)
-  int* const sr4c = (int*)(ws + L.r4c);
-  int* const sc4r = (int*)(ws + L.c4r);
-  int* const smask = (int*)(ws + L.path);                 // scratch [N]
-  const int col0 = (g < G ? g : 0) * A;
-  const unsigned gshift = (unsigned)base & 31u;
-  bool warm = valid && grp_live;                          // group-uniform
-  unsigned F = 0;                                         // free rows (group-uniform)
-  if (g == 0 && grp_live) { TEAM_STAT(0, 1); if (warm) TEAM_STAT(1, 1); }
-  if (__any_sync(FULL, warm)) {
-    // 1. Bellman-Ford re-centring of my column duals under the old matching
-#pragma unroll 1
-    for (int round = 0; round < 2; round++) {
-#pragma unroll
-      for (int a = 0; a < A; a++) {
-        const int r = sr4c[col0 + a];
-        if (warm && live) sw[r < 0 ? 0 : r] = v[a] - C[(r < 0 ? 0 : r) * N + col0 + a];
-      }
-      __syncwarp();
-      T t[A];
-#pragma unroll
-      for (int a = 0; a < A; a++) t[a] = v[a];
-#pragma unroll
-      for (int r = 0; r < N; r++) {
-        const T w = sw[r];
-#pragma unroll
-        for (int a = 0; a < A; a++) { const T c = w + C[r * N + col0 + a]; t[a] = c < t[a] ? c : t[a]; }
-      }
-#pragma unroll
-      for (int a = 0; a < A; a++) if (warm) v[a] = t[a];
-      __syncwarp();
-    }
-    // 2. row minima; rows whose matched edge no longer attains the minimum become free
-#pragma unroll 1
-    for (int r = 0; r < N; r++) {
-      T t[A], m = INF;
-#pragma unroll
-      for (int a = 0; a < A; a++) { t[a] = C[r * N + col0 + a] - v[a]; if (live) m = t[a] < m ? t[a] : m; }
-#pragma unroll
-      for (int s2 = GP / 2; s2 >= 1; s2 >>= 1) { const T o = __shfl_xor_sync(FULL, m, s2); m = o < m ? o : m; }
-      const int k = sc4r[r];
-      bool drop = false;
-#pragma unroll
-      for (int a = 0; a < A; a++) if (warm && live && col0 + a == k && !(t[a] == m)) drop = true;
-      const bool dropped = ((__ballot_sync(FULL, drop) >> gshift) & low_mask(GP)) != 0u || k < 0;
-      __syncwarp();
-      if (warm && live) {
-        if (drop) sr4c[k] = -1;
-        if (g == 0) { su[r] = m; if (dropped) sc4r[r] = -1; }
-      }
-      if (warm && dropped) F |= 1u << r;
-    }
-    __syncwarp();
-  }
-  // 3. one augmentation per free row — and, in a second pass, the cold scipy-order solve (all rows free, zero
-  //    duals, ascending order) of the groups that have no certified warm result: the first step of a launch,
-  //    ties.  ONE copy of lsa_augment serves both passes (two copies did not fit the instruction cache:
-  //    4.3 no-instruction stall cycles per issue, profiles/README.md).
-#pragma unroll 1
-  for (int pass = 0; pass < 2; pass++) {
-    if (pass == 1) {
-      const bool need_cold = grp_live && !warm;
-      const bool any_cold = __any_sync(FULL, need_cold);
-      if (g == 0 && need_cold) TEAM_STAT(3, 1);
-      if ((threadIdx.x & 31) == 0 && any_cold) TEAM_STAT(6, 1);
-      if (!any_cold) break;
-      F = need_cold ? low_mask(N) : 0u;
-      if (need_cold) {
-#pragma unroll
-        for (int a = 0; a < A; a++) {
-          v[a] = 0;
-          if (live) { su[col0 + a] = 0; sr4c[col0 + a] = -1; sc4r[col0 + a] = -1; }
-        }
-      }
-      __syncwarp();
-    } else if (g == 0) {
-      TEAM_STAT(4, __popc(F));
-    }
-    while (__any_sync(FULL, F != 0u)) {
-      if ((threadIdx.x & 31) == 0) TEAM_STAT(5, 1);
-      const bool act = F != 0u;
-      const int cur = act ? __ffs(F) - 1 : 0;
-      lsa_augment<T, N, G, GP>(C, ws, g, live, cur, act, v);
-      F &= F - 1u;
-    }
-    if (pass == 1 || !__any_sync(FULL, warm)) continue;
-    // 4. uniqueness certificate: the small-slack row graph must be acyclic
-    const T tol = (T)(16 * N) * (sizeof(T) == 4 ? (T)5.9604645e-8 : (T)1.1102230246251565e-16) * cmax;
-    int r4c_m[A];
-#pragma unroll
-    for (int a = 0; a < A; a++) { const int r = sr4c[col0 + a]; r4c_m[a] = r < 0 ? 0 : r; if (r < 0) warm = false; }
-#pragma unroll 1
-    for (int r = 0; r < N; r++) {
-      const T ur = su[r];
-      const int kr = sc4r[r];
-      unsigned bits = 0;
-#pragma unroll
-      for (int a = 0; a < A; a++) {
-        const T sl = C[r * N + col0 + a] - ur - v[a];
-        if (live && sl <= tol && col0 + a != kr) bits |= 1u << r4c_m[a];
-      }
-#pragma unroll
-      for (int s2 = GP / 2; s2 >= 1; s2 >>= 1) bits |= __shfl_xor_sync(FULL, bits, s2);
-      if (g == 0) smask[r] = (int)bits;
-    }
-    __syncwarp();
-    unsigned alive = low_mask(N);
-    for (int round = 0; round < N; round++) {
-      unsigned rem = 0;
-#pragma unroll
-      for (int r = 0; r < N; r++)
-        if (((alive >> r) & 1u) && ((unsigned)smask[r] & alive) == 0u) rem |= 1u << r;
-      alive &= ~rem;
-      if (!__any_sync(FULL, rem != 0u && alive != 0u)) break;
-    }
-    // an incomplete matching (non-finite costs) also fails
-    bool ok = warm && alive == 0u;
-#pragma unroll
-    for (int s2 = GP / 2; s2 >= 1; s2 >>= 1) ok = __shfl_xor_sync(FULL, (int)ok, s2) && ok;
-    if (g == 0 && valid && grp_live) { if (ok) TEAM_STAT(2, 1); else if (!warm) TEAM_STAT(7, 1); }
-    warm = ok;
-    __syncwarp();
-  }
-  valid = grp_live;
-#pragma unroll
-  for (int a = 0; a < A; a++) c4r_out[a] = live ? sc4r[col0 + a] : -1;
-}
-
 #ifndef GSM_TEAM_LSA2          // A/B: 1 = lsa_group2 (shared-memory solver state), 0 = lsa_group (registers)
 #define GSM_TEAM_LSA2 1
 #endif
-// A/B: 1 = fp32 steps after the first of a launch start from the previous duals / matching (lsa_warm).
-// Measured (profiles/README.md, round 2): parity-green, 98.5 % of the polygon-12 env-steps certified, 2.07 free
-// rows per env-step, 27 % fewer warp-instructions than the cold solve — and no faster: polygon-12 59.4 vs 60.8 us,
-// line-12 82.7 vs 71.3 (95.7 % certified: collinear slots make near-ties), polygon-6 17.8 vs 18.6, line-6 21.1 vs
-// 19.7.  The short dependent phases (row minima, certificate) hide no latency at 3.5 warps per scheduler and the
-// kernel grows to 86 KB of code.  Off by default.
-#ifndef GSM_TEAM_WARM
-#define GSM_TEAM_WARM 0
-#endif
+// A warm-started variant (Bellman-Ford re-centred duals, free rows, uniqueness certificate, cold fallback) was built
+// on lsa_augment, is parity-green and not faster: profiles/rejected/team_warm_start_lsa_r2.diff, profiles/README.md.
 
 constexpr int kTeamThreads = 128;
 
@@ -605,10 +434,6 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   unsigned char* c_done = (unsigned char*)p.done;
   unsigned char* c_asg = (unsigned char*)p.assign;
 
-  T lsa_v[A];                                             // warm start: my column duals, kept across the steps
-  bool lsa_valid = false;                                 // ... valid after the first solve of this launch
-#pragma unroll
-  for (int a = 0; a < A; a++) lsa_v[a] = 0;
   for (int step = 0; step < n_steps; step++) {
     // ---- SPEC §2-4 for my A agents (position table = state at the start of the step) ----------
 #pragma unroll
@@ -662,7 +487,6 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
 
     // ---- SPEC §5: slots of my A columns, cost columns, group-parallel assignment --------------
     T sx[A], sy[A];
-    T cmax = 0;                                            // largest cost of the env (scale of the warm start's certificate)
 #pragma unroll
     for (int a = 0; a < A; a++) {
       const int k = ga * A + a;
@@ -676,21 +500,13 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       }
       for (int r = 0; r < N && has; r++) {
         const T dx = sx[a] - apos[2 * r], dy = sy[a] - apos[2 * r + 1];
-        const T c = r_sqrt(dx * dx + dy * dy);
-        cmat[r * N + k] = c;
-        cmax = c > cmax ? c : cmax;
+        cmat[r * N + k] = r_sqrt(dx * dx + dy * dy);
       }
     }
     __syncwarp();
     int c4r[A];
 #if GSM_TEAM_LSA2
-    if (GSM_TEAM_WARM && sizeof(T) == 4) {
-#pragma unroll
-      for (int m = GP / 2; m >= 1; m >>= 1) { const T o = __shfl_xor_sync(0xffffffffu, cmax, m); cmax = o > cmax ? o : cmax; }
-      lsa_warm<T, N, G, GP>(cmat, (uint32_t*)(rsm + N), g, base, true, lsa_v, lsa_valid, cmax, c4r);
-    } else {
-      lsa_group2<T, N, G, GP>(cmat, (uint32_t*)(rsm + N), g, base, true, c4r);
-    }
+    lsa_group2<T, N, G, GP>(cmat, (uint32_t*)(rsm + N), g, base, true, c4r);
 #else
     lsa_group<T, N, G, GP>(cmat, g, base, true, c4r);
 #endif

@@ -379,19 +379,6 @@ int GSM_SFX(launch_team)(const HostParams& hp, const gsm_step_io& io, int n_step
   return -1;
 }
 
-// Diagnostics of the warm-started assignment (all zero unless built with -DGSM_TEAM_STATS=1); reset on read.
-int GSM_SFX(team_stats)(unsigned long long* out8) {
-#if GSM_TEAM_STATS
-  cudaError_t e = cudaMemcpyFromSymbol(out8, g_team_stats, 8 * sizeof(unsigned long long));
-  if (e != cudaSuccess) return (int)e;
-  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  return (int)cudaMemcpyToSymbol(g_team_stats, z, sizeof(z));
-#else
-  for (int k = 0; k < 8; k++) out8[k] = 0;
-  return 0;
-#endif
-}
-
 int GSM_SFX(launch_reset)(const HostParams& hp, uint64_t seed, const uint8_t* mask,
                           int64_t mask_stride, cudaStream_t st) {
   if (hp.n_envs == 0) return 0;

@@ -245,12 +245,6 @@ int gsm_get_state_host(gsm_env* h, void* agent_state, void* landmark_pos,
 /* Number of this library's kernels launched on behalf of the handle so far
  * (graph replays count the kernels inside the graph). */
 int64_t gsm_kernel_launches(const gsm_env* h);
-/* Diagnostics of the polygon / line kernel's warm-started assignment on the current device, reset on
- * read: [0] solves, [1] warm attempts, [2] certified warm results, [3] cold solves, [4] free rows,
- * [5] warp-level augmentation rounds, [6] warp-level cold runs, [7] incomplete matchings.  All zero
- * unless the library was built with -DGSM_TEAM_STATS=1 (profiles/ builds do that; the product build
- * does not count). */
-int gsm_debug_team_stats(uint64_t* out8);
 
 /* Stand-alone batched linear sum assignment (scipy.optimize.linear_sum_assignment,
  * scipy==1.7.3 in requirements.txt:101; rectangular_lsap shortest-augmenting-path,
