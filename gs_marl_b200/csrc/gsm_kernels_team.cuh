@@ -2,149 +2,23 @@
 // (SPEC.md §2-7; reference scenarios/simple_formation.py, simple_line.py — SOURCES.txt:24-25,
 // readme.md:89-90; scipy.optimize.linear_sum_assignment, requirements.txt:101).
 //
-// The assignment dominates these scenarios (profiles/README.md: 85 % of the instructions with
-// one lane per column and 2 problems per warp).  Here an env is served by a GROUP of G lanes
-// and every lane owns A = N / G agents, which are also its A assignment rows, A columns and A
-// slots of scipy's `remaining` order — so a warp solves 32 / G problems in lockstep (8 for
-// N = 12, 16 for N = 6, 32 for N <= 5) and all per-lane solver state (u, v, shortest-path
-// costs, path, row4col, col4row, positions) is statically indexed registers.  Group-wide
-// minimum / tie-rule maximum are log2(G) xor-shuffles; the tie rule of scipy's scan ("last
-// unassigned minimum in `remaining` order, else the first") is one max over packed keys.
-// Physics and the neighbour graph use the same layout (a lane sweeps the other agents for
-// each of its A agents from a shared-memory position table), rows go to HBM over a
-// warp-cooperative coalesced clear like in env_lane_kernel, and `n_steps` steps are fused.
+// The assignment dominates these scenarios (profiles/README.md: 74 % of the instructions).  An env is served
+// by a GROUP of G lanes (of a physical group of GP lanes, GP a power of two) and every lane owns A = N / G
+// agents, which are also its A assignment columns and rows — so a warp solves 32 / GP problems in lockstep
+// (8 for N = 12 with G = 4; 4 for N = 6 with one agent per lane, G = 6 of 8 lanes).  The solver
+// (lsa_augment / lsa_cold below) keeps the column duals, path costs, positions and tie keys of a lane's columns
+// in registers and everything that is indexed at run time in the env's shared-memory block; group-wide
+// minimum / tie-rule maximum are log2(GP) xor-shuffles.  Physics and the neighbour graph use the same layout
+// (a lane sweeps the other agents for each of its A agents from a shared-memory position table), rows go to
+// HBM over a warp-cooperative coalesced clear like in env_lane_kernel, and `n_steps` steps are fused.
 #pragma once
 #include "gsm_kernels_spec.cuh"
 
 namespace gsm {
 
-template <typename T, int A>
-__device__ __forceinline__ T sel(const T (&arr)[A], int idx) {
-  T r = arr[0];
-#pragma unroll
-  for (int a = 1; a < A; a++) r = idx == a ? arr[a] : r;
-  return r;
-}
-
-// scipy rectangular_lsap on N x N costs in shared memory, G lanes per problem, A = N / G rows
-// and columns per lane (row / column j belongs to lane j / A of the group, local index j % A).
-// Every lane of the warp calls it; groups are aligned runs of G lanes starting at `base`.
-// Returns col4row of the lane's A rows in c4r[].  Loops are bounded by N (no hang on NaN).
-// G lanes of a physical group of GP >= G lanes (GP a power of two) own the columns; lanes
-// g >= G of the group only take part in the warp primitives.  grp_live: the group holds a
-// problem; live = grp_live && g < G: this lane owns A rows / columns.
-template <typename T, int N, int G, int GP>
-__device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int base, bool grp_live,
-                                          int (&c4r)[N / G]) {
-  constexpr int A = N / G;
-  const bool live = grp_live && g < G;
-  constexpr unsigned FULL = 0xffffffffu;
-  const T INF = r_inf<T>();
-  T u[A], v[A], spc[A];
-  int path[A], r4c[A], pos[A];
-  bool inr[A];                                            // column still in scipy's `remaining`
-  const T* Cg = C + g * A;                                // my A columns of a cost row
-#pragma unroll
-  for (int a = 0; a < A; a++) { u[a] = 0; v[a] = 0; path[a] = -1; r4c[a] = -1; c4r[a] = -1; spc[a] = INF; pos[a] = 0; inr[a] = false; }
-  for (int cur = 0; cur < N; cur++) {
-    T minval = 0;
-    int i = cur, nrem = N, sink = grp_live ? -1 : 0;
-    unsigned sr = 0, sc = 0;
-#pragma unroll
-    for (int a = 0; a < A; a++) { spc[a] = INF; pos[a] = N - 1 - (g * A + a); inr[a] = live; }
-    for (int iter = 0; iter < N && __any_sync(FULL, sink == -1); iter++) {
-      const bool run = sink == -1;
-      const int ig = i / A, il = i - ig * A;
-      if (run && live && ig == g) sr |= 1u << il;
-      const T u_i = shfl(FULL, sel<T, A>(u, il), base + ig);
-      const T* Ci = Cg + i * N;
-      T lo = INF;
-#pragma unroll
-      for (int a = 0; a < A; a++) {
-        if (run && inr[a]) {
-          const T r = minval + Ci[a] - u_i - v[a];
-          if (r < spc[a]) { path[a] = i; spc[a] = r; }
-        }
-        const T cand = inr[a] ? spc[a] : INF;
-        lo = cand < lo ? cand : lo;
-      }
-#pragma unroll
-      for (int m = GP / 2; m >= 1; m >>= 1) {
-        const T o = __shfl_xor_sync(FULL, lo, m);
-        lo = o < lo ? o : lo;
-      }
-      // tie rule: an unassigned minimum with the largest position wins, else the minimum with
-      // the smallest position; positions are unique, the column index rides in the low bits
-      int best = -1;
-#pragma unroll
-      for (int a = 0; a < A; a++) {
-        const int key = r4c[a] == -1 ? 64 + pos[a] : 31 - pos[a];
-        const int packed = (inr[a] && spc[a] == lo) ? ((key << 6) | (g * A + a)) : -1;
-        best = packed > best ? packed : best;
-      }
-#pragma unroll
-      for (int m = GP / 2; m >= 1; m >>= 1) {
-        const int o = __shfl_xor_sync(FULL, best, m);
-        best = o > best ? o : best;
-      }
-      const int key = best >> 6, j = best < 0 ? 0 : (best & 63);
-      const int selpos = key >= 64 ? key - 64 : 31 - key;
-      const int jg = j / A, jl = j - jg * A;
-      const int r4c_j = shfl(FULL, sel<int, A>(r4c, jl), base + jg);
-      if (run && best >= 0) {
-        minval = lo;
-        if (r4c_j == -1) sink = j; else i = r4c_j;
-        nrem--;
-#pragma unroll
-        for (int a = 0; a < A; a++) {
-          if (live && jg == g && jl == a) { sc |= 1u << a; inr[a] = false; }
-          if (inr[a] && pos[a] == nrem) pos[a] = selpos;
-        }
-      }
-    }
-    // dual update (col4row as it was before this augmentation)
-#pragma unroll
-    for (int a = 0; a < A; a++) {
-      const int c = c4r[a] < 0 ? 0 : c4r[a];
-      const int cg = c / A, cl = c - cg * A;
-      T val = 0;
-#pragma unroll
-      for (int k = 0; k < A; k++) {
-        const T t = shfl(FULL, spc[k], base + cg);
-        if (cl == k) val = t;
-      }
-      if (live) {
-        if (g * A + a == cur) u[a] += minval;
-        else if ((sr >> a) & 1u) u[a] += minval - val;
-      }
-    }
-#pragma unroll
-    for (int a = 0; a < A; a++)
-      if ((sc >> a) & 1u) v[a] -= minval - spc[a];
-    // augment along the path
-    int j = sink < 0 ? 0 : sink;
-    bool going = grp_live && sink >= 0;
-    for (int iter = 0; iter < N && __any_sync(FULL, going); iter++) {
-      const int jg = j / A, jl = j - jg * A;
-      int arow = shfl(FULL, sel<int, A>(path, jl), base + jg);
-      arow = arow < 0 ? 0 : arow;
-      const int ag = arow / A, al = arow - ag * A;
-      const int tprev = shfl(FULL, sel<int, A>(c4r, al), base + ag);
-      if (going) {
-#pragma unroll
-        for (int a = 0; a < A; a++) {
-          if (jg == g && jl == a) r4c[a] = arow;
-          if (ag == g && al == a) c4r[a] = j;
-        }
-        j = tprev < 0 ? 0 : tprev;
-        if (arow == cur) going = false;
-      }
-    }
-  }
-}
-
-// ---- round 2: the same solver with a leaner lockstep iteration -------------------------------------------
-// lsa_group spends 165 instructions per Dijkstra iteration (profiles/ncu_r2_team_polygon12_lines.txt): select
+// ---- the group-parallel solver ------------------------------------------------------------------------------
+// Round 1's version (per-lane register arrays for everything; removed) spent 165 instructions per Dijkstra
+// iteration (profiles/ncu_r2_team_polygon12_lines.txt): select
 // chains that index per-lane register arrays with a run-time index (u[il], r4c[jl], path[jl]: 16), the relax
 // step behind divergent branches (38), tie keys rebuilt from scratch (22), boolean arrays (22), index splits by
 // A (11).  Here everything that is addressed by a run-time index — u, row4col, col4row, path and, after the
@@ -153,7 +27,9 @@ __device__ __forceinline__ void lsa_group(const T* __restrict__ C, int g, int ba
 // redundantly (i and j are group-uniform); the relax step is branch-free (a finished group runs with
 // minval = +inf, which can update nothing); the tie key of a column (unassigned: 64 + pos, assigned: 31 - pos,
 // column in the low bits) is kept in a register and touched only when its position or status changes.
-// Scan order and tie rule are lsa_group's, i.e. scipy's.
+// Scan order and tie rule are scipy's (rectangular_lsap, Crouse 2016): `remaining` filled in reverse with
+// swap-with-last removal is tracked as a per-column position, "last unassigned minimum in scan order, else the
+// first minimum" is one maximum over packed (key, column) words.
 struct TeamLsaSmem { int u, spc, r4c, c4r, path, words; };      // word offsets inside the env's solver block
 __host__ __device__ constexpr TeamLsaSmem team_lsa_smem(int rb, int N) {
   TeamLsaSmem t{};
@@ -169,42 +45,19 @@ __host__ __device__ constexpr TeamLsaSmem team_lsa_smem(int rb, int N) {
 
 // Minimum / maximum over the GP lanes of a group: log2(GP) xor-shuffle + compare stages.  The alternative — ONE
 // redux.sync over the group's lane mask (order-preserving integer key for the float) — is 2.3x SLOWER end to end
-// (polygon-12 137 vs 60 us per step, -DGSM_TEAM_REDUX=1): a redux.sync over a sub-warp mask is executed once per
+// (polygon-12 137 vs 60 us per step, measured in round 2): a redux.sync over a sub-warp mask is executed once per
 // distinct mask, i.e. 8 times per warp here.
-#ifndef GSM_TEAM_REDUX
-#define GSM_TEAM_REDUX 0
-#endif
-template <int GP>
-__device__ __forceinline__ float group_min(float v, unsigned gmask) {
-#if GSM_TEAM_REDUX
-  if (GP > 1) {
-    const unsigned b = __float_as_uint(v);
-    const unsigned key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-    const unsigned r = __reduce_min_sync(gmask, key);
-    return __uint_as_float((r & 0x80000000u) ? (r & 0x7fffffffu) : ~r);
-  }
-  return v;
-#else
+template <int GP, typename T>
+__device__ __forceinline__ T group_min(T v, unsigned) {
 #pragma unroll
-  for (int m = GP / 2; m >= 1; m >>= 1) { const float o = __shfl_xor_sync(0xffffffffu, v, m); v = o < v ? o : v; }
-  return v;
-#endif
-}
-template <int GP>
-__device__ __forceinline__ double group_min(double v, unsigned) {
-#pragma unroll
-  for (int m = GP / 2; m >= 1; m >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, v, m); v = o < v ? o : v; }
+  for (int m = GP / 2; m >= 1; m >>= 1) { const T o = __shfl_xor_sync(0xffffffffu, v, m); v = o < v ? o : v; }
   return v;
 }
 template <int GP>
-__device__ __forceinline__ int group_max(int v, unsigned gmask) {
-#if GSM_TEAM_REDUX
-  return GP > 1 ? __reduce_max_sync(gmask, v) : v;
-#else
+__device__ __forceinline__ int group_max(int v, unsigned) {
 #pragma unroll
   for (int m = GP / 2; m >= 1; m >>= 1) { const int o = __shfl_xor_sync(0xffffffffu, v, m); v = o > v ? o : v; }
   return v;
-#endif
 }
 
 // One shortest-augmenting-path step for row `cur` of every ACTIVE group, in lockstep: Dijkstra search from
@@ -347,9 +200,6 @@ __device__ __forceinline__ void lsa_group2(const T* __restrict__ C, uint32_t* __
   for (int a = 0; a < A; a++) c4r_out[a] = live ? ((const int*)(ws + L.c4r))[col0 + a] : -1;
 }
 
-#ifndef GSM_TEAM_LSA2          // A/B: 1 = lsa_group2 (shared-memory solver state), 0 = lsa_group (registers)
-#define GSM_TEAM_LSA2 1
-#endif
 // A warm-started variant (Bellman-Ford re-centred duals, free rows, uniqueness certificate, cold fallback) was built
 // on lsa_augment, is parity-green and not faster: profiles/rejected/team_warm_start_lsa_r2.diff, profiles/README.md.
 
@@ -505,11 +355,7 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     }
     __syncwarp();
     int c4r[A];
-#if GSM_TEAM_LSA2
     lsa_group2<T, N, G, GP>(cmat, (uint32_t*)(rsm + N), g, base, true, c4r);
-#else
-    lsa_group<T, N, G, GP>(cmat, g, base, true, c4r);
-#endif
     __syncwarp();
 
     // ---- padding first: the rows of this warp's envs are one contiguous region -------------------
