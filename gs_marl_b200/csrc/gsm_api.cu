@@ -218,16 +218,13 @@ int do_steps(gsm_env* h, const gsm_step_io& io, int n_steps, cudaStream_t st, in
   else if (h->plan.lane && !observe)
     e = is_f32(h) ? gsm::launch_lane_f32(h->hp, io, n_steps, rs, st)
                   : gsm::launch_lane_f64(h->hp, io, n_steps, rs, st);
-  else if (h->plan.big && !observe)
-    e = is_f32(h) ? gsm::launch_big_f32(h->hp, io, n_steps, rs, st)
-                  : gsm::launch_big_f64(h->hp, io, n_steps, rs, st);
   if (e > 0) return cuda_fail(h, e, "fused env kernel launch");
   if (e == 0) { h->launches += 1; return 0; }
   return -1000;      // no fused kernel for this handle / call
 }
 
 int do_step(gsm_env* h, const gsm_step_io& io, cudaStream_t st) {
-  if (h->plan.spec || h->plan.big || h->plan.lane) {
+  if (h->plan.spec || h->plan.lane) {
     const int r = do_steps(h, io, 1, st);
     if (r != -1000) return r;
   }
@@ -603,7 +600,7 @@ int gsm_rollout(gsm_env* h, int32_t n_steps, const gsm_step_io* io, void* stream
   DeviceGuard guard(h->device);
   // fused: all n_steps in one launch, state stays on chip; the specialised and the lane kernel
   // also re-draw finished envs in the kernel (auto-reset)
-  if (h->plan.spec || h->plan.lane || (h->plan.big && !h->auto_reset)) {
+  if (h->plan.spec || h->plan.lane) {
     h->hp.auto_reset = h->auto_reset; h->hp.seed = h->seed;
     const int r = do_steps(h, *io, n_steps, (cudaStream_t)stream);
     h->hp.auto_reset = 0;

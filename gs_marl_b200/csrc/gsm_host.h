@@ -42,7 +42,6 @@ struct LaunchPlan {     // chosen once per handle
   size_t smem;
   int64_t grid;
   int spec;             // 1: a size-specialised register-resident kernel exists (gsm_kernels_spec.cuh)
-  int big;              // 1: the large-team CTA-per-env kernel applies (gsm_kernels_big.cuh)
   int lane;             // 1: the lane-per-agent kernel applies (gsm_kernels_lane.cuh)
   int team;             // 1: a polygon/line group-LSA instance exists (gsm_kernels_team.cuh)
 };
@@ -63,11 +62,6 @@ int launch_spec_f32(const HostParams& hp, const gsm_step_io& io, int n_steps,
 int launch_spec_f64(const HostParams& hp, const gsm_step_io& io, int n_steps,
                     const RolloutStrides& rs, int observe, const uint8_t* mask,
                     int64_t mask_stride, cudaStream_t st);
-// Large-team navigation kernel (n_steps fused); returns -1 if it does not apply.
-int launch_big_f32(const HostParams& hp, const gsm_step_io& io, int n_steps,
-                   const RolloutStrides& rs, cudaStream_t st);
-int launch_big_f64(const HostParams& hp, const gsm_step_io& io, int n_steps,
-                   const RolloutStrides& rs, cudaStream_t st);
 // Lane-per-agent navigation kernel (n_steps fused); returns -1 if it does not apply.
 int launch_lane_f32(const HostParams& hp, const gsm_step_io& io, int n_steps,
                     const RolloutStrides& rs, cudaStream_t st);

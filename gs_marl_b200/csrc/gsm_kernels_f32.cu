@@ -1,5 +1,4 @@
 // Production precision (fp32).  FMA contraction allowed.
-#include "gsm_kernels_big.cuh"
 #include "gsm_kernels_lane.cuh"
 #include "gsm_kernels_team.cuh"
 #include "gsm_kernels_wide.cuh"

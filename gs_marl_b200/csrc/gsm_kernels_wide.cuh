@@ -30,7 +30,7 @@
 // deviation 6).  History and measurements: profiles/README.md, round 2.
 #pragma once
 #include "gsm_kernels_spec.cuh"
-#include "gsm_kernels_big.cuh"   // bulk-store helpers
+#include "gsm_bulk.cuh"
 
 namespace gsm {
 

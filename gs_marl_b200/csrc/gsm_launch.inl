@@ -11,7 +11,6 @@ static int env_int(const char* name, int dflt) {
 }
 
 static bool has_spec(const HostParams& hp);
-static bool has_big(const HostParams& hp);
 static bool has_lane(const HostParams& hp);
 static bool has_team(const HostParams& hp);
 static int next_pow2(int v) { int p = 1; while (p < v) p *= 2; return p; }
@@ -45,11 +44,9 @@ int GSM_SFX(plan)(const HostParams& hp, LaunchPlan* plan) {
   if (plan->smem > 227 * 1024) return (int)cudaErrorInvalidValue;
   plan->spec = has_spec(hp) ? 1 : 0;
   plan->team = has_team(hp) ? 1 : 0;   // polygon / line steps; observe stays on the specialised kernel
-  // preference: lane-per-agent (N >= GSM_LANE_MIN_N) > specialised > CTA-per-env > generic
+  // preference: lane-per-agent (N >= GSM_LANE_MIN_N) > specialised (wide instance first) > generic
   plan->lane = has_lane(hp) ? 1 : 0;
   if (plan->lane) plan->spec = 0;
-  plan->big = (!plan->lane && (!plan->spec || env_int("GSM_BIG_MIN_N", 13) <= hp.N) && has_big(hp)) ? 1 : 0;
-  if (plan->big) plan->spec = 0;
   return 0;
 }
 
@@ -250,38 +247,6 @@ int GSM_SFX(launch_spec)(const HostParams& hp, const gsm_step_io& io, int n_step
   GSM_SPEC_TABLE(X)
 #undef X
   return -1;
-}
-
-// ---- large-team kernel (gsm_kernels_big.cuh) -------------------------------------------------
-static size_t big_smem(const HostParams& hp) {
-  return make_big_layout((int)sizeof(GSM_REAL), (int)sizeof(Ent<GSM_REAL>), hp.N, hp.N + hp.L, hp.K,
-                         kBigThreads / 32).total;
-}
-static bool has_big(const HostParams& hp) {
-  if (env_int("GSM_NO_BIG", 0) != 0 || env_int("GSM_FORCE_P", 0) != 0 || env_int("GSM_FORCE_CTA_ENV", -1) >= 0)
-    return false;
-  return hp.scenario == GSM_SCN_NAVIGATION && hp.N >= env_int("GSM_BIG_MIN_N", 13) && hp.K % 4 == 0 &&
-         big_smem(hp) <= 200 * 1024;
-}
-
-int GSM_SFX(launch_big)(const HostParams& hp, const gsm_step_io& io, int n_steps,
-                        const RolloutStrides& rs, cudaStream_t st) {
-  if (!has_big(hp)) return -1;
-  if (hp.n_envs == 0) return 0;
-  KParams<GSM_REAL> kp;
-  fill_kparams(kp, hp, io, 0, nullptr, 0);
-  StepStrides ss;
-  ss.actions = rs.actions; ss.obs = rs.obs; ss.nbr_idx = rs.nbr_idx; ss.nbr_feat = rs.nbr_feat;
-  ss.nbr_cnt = rs.nbr_cnt; ss.adj = rs.adj; ss.reward = rs.reward; ss.cost = rs.cost;
-  ss.done = rs.done; ss.assign = rs.assign;
-  const size_t smem = big_smem(hp);
-  auto k = env_big_kernel<GSM_REAL>;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-  }
-  k<<<(unsigned)hp.n_envs, kBigThreads, smem, st>>>(kp, n_steps, ss);
-  return (int)cudaGetLastError();
 }
 
 // ---- lane-per-agent kernel (gsm_kernels_lane.cuh) ----------------------------------------------

@@ -143,21 +143,14 @@ def test_specialised_kernel_variants_f64(name, N, P, kw, monkeypatch):
     env.close()
 
 
-@pytest.mark.parametrize("which", ["lane", "big"])
 @pytest.mark.parametrize("N,K,B,kw", [(24, 16, 9, {}), (48, 32, 5, {"share_reward": True}),
                                       (96, 32, 3, {"action_mode": "continuous"}), (13, 4, 11, {}),
                                       (12, 32, 37, {}), (24, 7, 6, {"own_goal_always": False}),
                                       (33, 64, 4, {"n_obstacles": 0, "cost_obstacles": False})])
-def test_large_team_kernel_fused_f64(N, K, B, kw, which, monkeypatch):
-    """The two large-team kernels — env_lane_kernel (lane per agent) and env_big_kernel (CTA per
-    env, TMA bulk stores): one fused 10-step launch and single steps against the oracle."""
-    if which == "big":
-        monkeypatch.setenv("GSM_NO_LANE", "1")
-        monkeypatch.setenv("GSM_BIG_MIN_N", "12")
-        if K % 4:
-            pytest.skip("bulk stores need K % 4 == 0")
-    else:
-        monkeypatch.setenv("GSM_LANE_MIN_N", "12")
+def test_large_team_kernel_fused_f64(N, K, B, kw, monkeypatch):
+    """env_lane_kernel (lane per agent; teams of 12 ... 96, one or several warps per env): one fused
+    10-step launch and single steps against the oracle."""
+    monkeypatch.setenv("GSM_LANE_MIN_N", "12")
     cfg = make_cfg("navigation", N, "f64", max_nbrs=K, **kw)
     T = 10
     o = _squeezed_start(cfg, B, 5 + N)
@@ -171,12 +164,12 @@ def test_large_team_kernel_fused_f64(N, K, B, kw, which, monkeypatch):
     assert env.kernel_launches == 1                      # fused, not a graph of T launches
     for t in range(T):
         assert_match({k: roll[k][t] for k in OUT_KEYS}, wants[t], rtol=F64_RTOL, atol=F64_ATOL,
-                     ctx=f"nav{N} big fused t={t}")
+                     ctx=f"nav{N} lane fused t={t}")
     np.testing.assert_allclose(env.get_state()[0].cpu().numpy(), o.agent_state, rtol=F64_RTOL, atol=F64_ATOL)
     env.set_state(s0, o.landmark_pos, np.zeros(B, np.int32))
     for t in range(2):
         env.step(acts[t])
-        assert_match(_np(env.buf), wants[t], rtol=F64_RTOL, atol=F64_ATOL, ctx=f"nav{N} big step t={t}")
+        assert_match(_np(env.buf), wants[t], rtol=F64_RTOL, atol=F64_ATOL, ctx=f"nav{N} lane step t={t}")
     env.close()
 
 
