@@ -115,7 +115,7 @@ __host__ __device__ constexpr WideSmem wide_smem_layout(int rb, int N, int E, in
   WideSmem w{};
   unsigned o = 0;
   w.feat = o; o += (unsigned)(EPW * N * K * GSM_NBR_FEAT_DIM * rb);
-  w.idx = o; o += (unsigned)(EPW * N * K * 4);
+  w.idx = o; o += ((unsigned)(EPW * N * K * 4) + 15u) & ~15u;    // N = 5 with odd K: pad, the vector stores below need 16
   w.obs = o; o += (unsigned)(EPW * N * GSM_OBS_DIM * rb);
   w.cnt = o; o += (unsigned)(EPW * N * 4);
   w.adj = o; o += (unsigned)(EPW * N * 4);
@@ -148,10 +148,13 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int RB = (int)sizeof(T);
   constexpr int RS4 = EPW * N * 4, RST = EPW * N * RB;      // bytes of a per-agent 4-byte / real block of the warp
-  constexpr int PC4 = RS4 / 16, PCT = RST / 16, NPIECE = 3 * PC4 + 2 * PCT;
+  // the per-agent scalar blocks of a warp-step leave in PS-byte pieces, one per lane (16 where the blocks allow, else 8)
+  constexpr int PS = (RS4 % 16 == 0 && RST % 16 == 0) ? 16 : 8;
+  constexpr int PC4 = RS4 / PS, PCT = RST / PS, NPIECE = 3 * PC4 + 2 * PCT;
+  constexpr bool ROLE_OK = NPIECE <= 32;                   // else (N = 5 in fp64): the word-wise path
   static_assert(GW <= 32 && E <= 32, "an env must fit in one warp, adjacency in one word");
   static_assert(L >= N && 2 * N <= GW + 1 && N >= 3, "goal i is landmark i, held by lane N-1+i; lanes 0..2 stage scalars");
-  static_assert(RS4 % 16 == 0 && NPIECE <= 32, "per-warp scalar blocks leave in 16-byte pieces, one per lane");
+  static_assert(RS4 % 8 == 0 && RST % 8 == 0, "per-warp scalar blocks leave in 8- or 16-byte pieces");
   static_assert(EPW * N * M * 4 / 16 <= 64 && EPW * N * GSM_OBS_DIM * RB / 16 <= 64, "idx / obs blocks leave in <= 2 passes");
   typedef Arith<T> A;
   typedef WideEnt<T> Ent;
@@ -170,7 +173,7 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   const int ja = own ? j : 0;
   const unsigned act_bits = __ballot_sync(FULL, active);
   // staged bulk path: the warp's EPW envs all exist (and are unmasked) and every slot is 16-byte aligned
-  const bool bulk = act_bits == FULL &&
+  const bool bulk = ROLE_OK && act_bits == FULL && ((EPW * N * K * 4) & 15) == 0 &&
       ((((uintptr_t)p.obs | (uintptr_t)p.nbr_idx | (uintptr_t)p.nbr_feat | (uintptr_t)p.nbr_cnt | (uintptr_t)p.adj |
          (uintptr_t)p.assign | (uintptr_t)p.reward | (uintptr_t)p.cost | (uintptr_t)ss.obs | (uintptr_t)ss.nbr_idx |
          (uintptr_t)ss.nbr_feat | (uintptr_t)ss.nbr_cnt | (uintptr_t)ss.adj | (uintptr_t)ss.assign |
@@ -220,11 +223,11 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   int64_t role_stride = ss.nbr_cnt;                      // fp32: one stride for all five (launcher-checked)
   {
     const int q = lane;
-    if (q < PC4) c_role = (unsigned char*)p.nbr_cnt + wrow0 * 4u + q * 16;
-    else if (q < 2 * PC4) { c_role = (unsigned char*)p.adj + wrow0 * 4u + (q - PC4) * 16; if (RB != 4) role_stride = ss.adj; }
-    else if (q < 2 * PC4 + PCT) { c_role = (unsigned char*)p.cost + wrow0 * (unsigned)RB + (q - 2 * PC4) * 16; if (RB != 4) role_stride = ss.cost; }
-    else if (q < 2 * PC4 + 2 * PCT) { c_role = (unsigned char*)p.reward + wrow0 * (unsigned)RB + (q - 2 * PC4 - PCT) * 16; if (RB != 4) role_stride = ss.reward; }
-    else if (q < NPIECE) { c_role = (unsigned char*)p.assign + wrow0 * 4u + (q - 2 * PC4 - 2 * PCT) * 16; if (RB != 4) role_stride = ss.assign; }
+    if (q < PC4) c_role = (unsigned char*)p.nbr_cnt + wrow0 * 4u + q * PS;
+    else if (q < 2 * PC4) { c_role = (unsigned char*)p.adj + wrow0 * 4u + (q - PC4) * PS; if (RB != 4) role_stride = ss.adj; }
+    else if (q < 2 * PC4 + PCT) { c_role = (unsigned char*)p.cost + wrow0 * (unsigned)RB + (q - 2 * PC4) * PS; if (RB != 4) role_stride = ss.cost; }
+    else if (q < 2 * PC4 + 2 * PCT) { c_role = (unsigned char*)p.reward + wrow0 * (unsigned)RB + (q - 2 * PC4 - PCT) * PS; if (RB != 4) role_stride = ss.reward; }
+    else if (q < NPIECE) { c_role = (unsigned char*)p.assign + wrow0 * 4u + (q - 2 * PC4 - 2 * PCT) * PS; if (RB != 4) role_stride = ss.assign; }
   }
   const bool role_on = lane < NPIECE && (!OBS || lane < 2 * PC4 || lane >= 2 * PC4 + 2 * PCT);
   // assign[i] = i never changes: both staging buffers get it once
@@ -400,7 +403,14 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         if (lane + 32 < n_idx) g_idx[32] = lds16(s_idx + 512);
         if (lane < n_obs) g_obs[0] = lds16(s_obs);
         if (lane + 32 < n_obs) g_obs[32] = lds16(s_obs + 512);
-        if (role_on) *(V*)c_role = lds16(sb + lay.cnt + (unsigned)lane * 16u);
+        if (role_on) {
+          if (PS == 16) *(V*)c_role = lds16(sb + lay.cnt + (unsigned)lane * 16u);
+          else {
+            float2 v8;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v8.x), "=f"(v8.y) : "r"(sb + lay.cnt + (unsigned)lane * 8u) : "memory");
+            *(float2*)c_role = v8;
+          }
+        }
       } else {
         // ragged / masked / unaligned warps: word-wise, per-env predicated
         __syncwarp();
@@ -413,7 +423,7 @@ env_wide_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
             }
         };
         copy_words(b_feat + wrow0 * (unsigned)(K * GSM_NBR_FEAT_DIM * RB), lay.feat, lay.idx - lay.feat);
-        copy_words(b_idx + wrow0 * (unsigned)(K * 4), lay.idx, lay.obs - lay.idx);
+        copy_words(b_idx + wrow0 * (unsigned)(K * 4), lay.idx, (unsigned)(EPW * N * K * 4));
         copy_words(b_obs + wrow0 * (unsigned)(GSM_OBS_DIM * RB), lay.obs, lay.cnt - lay.obs);
         copy_words((unsigned char*)p.nbr_cnt + (int64_t)step * ss.nbr_cnt + wrow0 * 4u, lay.cnt, RS4);
         copy_words((unsigned char*)p.adj + (int64_t)step * ss.adj + wrow0 * 4u, lay.adj, RS4);

@@ -159,7 +159,8 @@ static int spec_P(const HostParams& hp) {
   return first;
 }
 
-static bool has_spec(const HostParams& hp) { return spec_P(hp) != 0; }
+static bool has_wide(const HostParams& hp);
+static bool has_spec(const HostParams& hp) { return spec_P(hp) != 0 || has_wide(hp); }
 
 template <int SCN, int N, int L, int P>
 static int launch_spec_one(const KParams<GSM_REAL>& kp, int n_steps, const StepStrides& ss,
@@ -179,7 +180,7 @@ static int launch_spec_one(const KParams<GSM_REAL>& kp, int n_steps, const StepS
 // ---- one-lane-per-other navigation kernel (gsm_kernels_wide.cuh) ---------------------------------
 // (N, L) instances; preferred over the (N*P lanes per env) specialised kernel where one exists.
 // K: max_nbrs the instance is compiled for (0: any, read at run time)
-#define GSM_WIDE_TABLE(X) X(3, 6, 8) X(3, 6, 0)
+#define GSM_WIDE_TABLE(X) X(3, 6, 8) X(3, 6, 0) X(4, 8, 0) X(5, 10, 0)
 
 static bool has_wide(const HostParams& hp) {
   if (!spec_enabled() || env_int("GSM_NO_WIDE", 0) != 0 || env_int("GSM_SPEC_P", 0) != 0) return false;
@@ -227,7 +228,7 @@ int GSM_SFX(launch_spec)(const HostParams& hp, const gsm_step_io& io, int n_step
                          const RolloutStrides& rs, int observe, const uint8_t* mask,
                          int64_t mask_stride, cudaStream_t st) {
   const int P = spec_P(hp);
-  if (!P) return -1;
+  if (!P && !has_wide(hp)) return -1;
   if (hp.n_envs == 0) return 0;
   KParams<GSM_REAL> kp;
   fill_kparams(kp, hp, io, 0, mask, mask_stride);

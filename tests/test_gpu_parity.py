@@ -813,13 +813,16 @@ WIDE_VARIANTS = [{}, {"share_reward": True}, {"own_goal_always": False}, {"cost_
 
 @pytest.mark.parametrize("kw", WIDE_VARIANTS)
 @pytest.mark.parametrize("B", [1, 3, 130, 257])
-def test_wide_kernel_variants_f64(kw, B):
+@pytest.mark.parametrize("N", [3, 4, 5])
+def test_wide_kernel_variants_f64(kw, B, N):
     """env_wide_kernel (navigation-3: one lane per other entity, shared-memory entity table, staged outputs,
     bulk copies) on every scenario switch, on max_nbrs below / at the number of others (the run-time-K
     instance and the K = 8 instance), and on ragged batches (warps with 1..3 of 4 envs take the word-wise
-    copy path): fused 25 steps with in-kernel auto-reset, single steps and observe against the oracle."""
+    copy path): fused 25 steps with in-kernel auto-reset, single steps and observe against the oracle.
+    N = 4 (11 others on 16 lanes, 2 envs per warp) exercises the instance whose groups have idle lanes, N = 5
+    the 8-byte scalar pieces (fp32) and the word-wise copy path for every warp (fp64: 35 pieces > 32 lanes)."""
     from oracle import gsm_oracle as O
-    cfg = make_cfg("navigation", 3, "f64", episode_length=7, **kw)
+    cfg = make_cfg("navigation", N, "f64", episode_length=7, **kw)
     seed, T = 5 + B, 25
     o = O.OracleEnv(cfg, B)
     o.reset(seed)
@@ -854,6 +857,37 @@ def test_wide_kernel_variants_f64(kw, B):
         want = o.step(a1)
         env.step(a1)
         assert_match(_np(env.buf), want, rtol=F64_RTOL, atol=F64_ATOL, ctx=f"wide {kw} single step {t}")
+    env.close()
+
+
+@pytest.mark.parametrize("N", [4, 5])
+def test_wide_kernel_f32_small_teams_vs_oracle(N):
+    """fp32 instances of the wide kernel for N = 4 / 5 (16-byte / 8-byte scalar pieces, bulk feature copies):
+    one fused launch against the fp32 oracle on rows away from contacts and thresholds."""
+    from oracle import gsm_oracle as O
+    cfg = make_cfg("navigation", N, "f32")
+    B, T = 258, 6
+    o = O.OracleEnv(cfg, B)
+    o.reset(3)
+    env = _env(cfg, B)
+    env.set_state(o.agent_state, o.landmark_pos, o.step_count)
+    acts = random_actions(cfg, np.random.default_rng(N), (T, B))
+    out = _np(env.rollout(acts))
+    touched, _ = _contact_touched(cfg, o.agent_state, o.landmark_pos, 0.03)
+    clean = ~touched
+    checked = 0
+    for t in range(T):
+        want = o.step(acts[t])
+        touched, d_aa = _contact_touched(cfg, o.agent_state, o.landmark_pos, 0.03)
+        clean &= ~touched
+        dirty_near = ((d_aa < cfg.sensing_radius + 0.5) & ~clean[:, None, :]).any(2)
+        ok = clean & ~dirty_near & ~near_threshold_rows(cfg, o.agent_state, o.landmark_pos, 1e-4)
+        for k in ("nbr_cnt", "cost", "nbr_idx", "adj", "done", "assign"):
+            assert (out[k][t][ok] == want[k][ok]).all(), (N, t, k)
+        for k in ("obs", "nbr_feat", "reward"):
+            np.testing.assert_allclose(out[k][t][ok], want[k][ok], rtol=1e-4, atol=2e-5, err_msg=f"nav{N} t={t} {k}")
+        checked += int(ok.sum())
+    assert checked > 0.05 * T * B * N
     env.close()
 
 
