@@ -32,6 +32,8 @@ CONFIGS = [  # (label, scenario, N, n_envs, kwargs)
     ("cfg4 nav-12 x8192 (65536/8 GPUs)", "navigation", 12, 8192, {}),
     ("cfg4 nav-12 x65536", "navigation", 12, 65536, {}),
     ("nav-6 x16384", "navigation", 6, 16384, {}),
+    ("nav-4 x16384", "navigation", 4, 16384, {}),
+    ("nav-5 x16384", "navigation", 5, 16384, {}),
 ]
 
 
