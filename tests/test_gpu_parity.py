@@ -476,6 +476,40 @@ def test_full_size_properties_config1():
     env.close()
 
 
+@pytest.mark.parametrize("name,N,B,kw", [
+    ("navigation", 24, 4096, {"max_nbrs": 32}), ("navigation", 48, 4096, {"max_nbrs": 32}),
+    ("navigation", 96, 4096, {"max_nbrs": 32}),                      # configs[2]
+    ("polygon", 6, 16384, {}), ("polygon", 12, 16384, {}), ("line", 6, 16384, {}), ("line", 12, 16384, {}),   # configs[3]
+    ("navigation", 12, 8192, {}),                                    # configs[4], one GPU's share of 65536
+])
+def test_full_size_other_baseline_configs(name, N, B, kw):
+    """BASELINE configs[2..4] at their full per-GPU batch, fp64 verification: one fused 2-step launch with
+    the episode end in between (in-kernel re-draw) against the oracle in full, every output."""
+    from oracle import gsm_oracle as O
+    cfg = make_cfg(name, N, "f64", episode_length=2, **kw)
+    O.set_threads(os.cpu_count() or 1)
+    try:
+        o = O.OracleEnv(cfg, B)
+        o.reset(9)
+        o.step_count[:] = np.arange(B) % 2                          # half of the envs re-draw after step 0
+        env = _env(cfg, B, seed=9)
+        env.reset()
+        env.set_state(None, None, o.step_count)
+        T = 2
+        acts = random_actions(cfg, np.random.default_rng(N), (T, B))
+        roll = env.rollout(acts, auto_reset=True)
+        for t in range(T):
+            want = o.step(acts[t])
+            got = _np({k: roll[k][t] for k in OUT_KEYS})
+            assert_match(got, want, rtol=F64_RTOL, atol=F64_ATOL, ctx=f"{name}{N}x{B} t={t}")
+            if want["done"].any():
+                o.reset(9, want["done"][:, 0].copy())
+        del roll
+        env.close()
+    finally:
+        O.set_threads(1)
+
+
 # ---- edge cases through the raw C ABI ------------------------------------------------------
 def test_out_of_range_actions_mean_no_control():
     """SPEC §2: a discrete index outside the table is u = 0 (both kernels, both precisions)."""
