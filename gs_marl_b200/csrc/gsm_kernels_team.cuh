@@ -355,7 +355,12 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     }
     __syncwarp();
     int c4r[A];
+#ifdef GSM_TEAM_NO_LSA   // diagnostic build only (profiles/README.md): what the step costs without the solve
+#pragma unroll
+    for (int a = 0; a < A; a++) c4r[a] = ga * A + a;
+#else
     lsa_group2<T, N, G, GP>(cmat, (uint32_t*)(rsm + N), g, base, true, c4r);
+#endif
     __syncwarp();
 
     // ---- padding first: the rows of this warp's envs are one contiguous region -------------------
