@@ -696,7 +696,7 @@ int gsm_set_host_outputs(gsm_env* h, uint32_t out_mask, int32_t sparse) {
   if (!h) return GSM_ERR_INVALID_ARG;
   out_mask |= 1u << IO_ACTIONS;
   out_mask |= ~((1u << IO_COUNT) - 1u);                      // unknown bits read as "on": 0xffffffff stays "everything"
-  if (out_mask != h->host_out_mask || (sparse != 0) != (h->host_sparse != 0)) h->host_resync = 1;
+  h->host_resync = 1;                                        // every call: also the way to recover an overwritten host arena
   h->host_out_mask = out_mask;
   h->host_sparse = sparse != 0;
   return GSM_OK;
@@ -709,7 +709,7 @@ int gsm_reset_host(gsm_env* h, uint64_t seed, const uint8_t* mask, int64_t mask_
   int st = ensure_host_path(h);
   if (st) return st;
   const uint8_t* dmask = nullptr;
-  if (mask && io && any_obs_output(*io) && !is_arena_io(h, *io))
+  if (mask && io && any_obs_output(*io) && !is_arena_io(h, *io))   // checked BEFORE anything is mutated: an error call has no side effect
     return fail(h, GSM_ERR_UNSUPPORTED, "masked gsm_reset_host needs the gsm_host_io buffers (partial rows are kept on the device copy)");
   if (mask) {
     if (mask_stride < 1 || mask_stride > h->hp.N) return fail(h, GSM_ERR_INVALID_ARG, "host mask_stride must be in [1, N]");
@@ -718,8 +718,6 @@ int gsm_reset_host(gsm_env* h, uint64_t seed, const uint8_t* mask, int64_t mask_
     dmask = h->d_mask;
   }
   const bool want = io && any_obs_output(*io);
-  if (want && mask && !is_arena_io(h, *io))      // checked BEFORE anything is mutated: an error call has no side effect
-    return fail(h, GSM_ERR_UNSUPPORTED, "masked gsm_reset_host needs the gsm_host_io buffers (partial rows are kept on the device copy)");
   st = gsm_reset(h, seed, dmask, mask_stride, want ? &h->d_io : nullptr, h->stream);
   if (st) return st;
   if (!want) { GSM_CUDA(h, cudaStreamSynchronize(h->stream)); return GSM_OK; }

@@ -30,7 +30,8 @@ def shard_bounds(n_envs_total: int, world_size: int, rank: int) -> Tuple[int, in
 
 class GraphVecEnv:
     """numpy drop-in over gsm_*_host.  Returned arrays are views of the pinned arena and
-    are overwritten by the next call (copy them to keep them)."""
+    are overwritten by the next call (copy them to keep them).  The output views are READ-ONLY: the
+    sparse export (`set_host_outputs`) sends only what differs from what the arena already holds."""
 
     def __init__(self, world: WorldConfig, n_envs: int, device: int = 0, env_offset: int = 0,
                  auto_reset: bool = False, seed: int = 0):
@@ -48,6 +49,8 @@ class GraphVecEnv:
             nbytes = int(np.prod(shape)) * np.dtype(dt).itemsize
             raw = (C.c_char * nbytes).from_address(getattr(self._io, k))
             self.buf[k] = np.frombuffer(raw, dtype=dt).reshape(shape)
+            if k != "actions":
+                self.buf[k].flags.writeable = False
         self.num_envs = self.n_envs
         self.n = world.n_agents
 
@@ -91,10 +94,11 @@ class GraphVecEnv:
         self._check(self.lib.gsm_step_host(self._h, C.byref(self._io)))
         b = self.buf
         if self.auto_reset and b["done"].any():
-            rew, cost, done = b["reward"].copy(), b["cost"].copy(), b["done"].copy()
+            # the re-draw refreshes obs / graph of the finished envs; reward, cost and done are not outputs of a
+            # reset and keep the terminal step's values in the arena
+            done = b["done"].copy()
             self._check(self.lib.gsm_reset_host(self._h, self._seed, done.ctypes.data,
                                                 self.world.n_agents, C.byref(self._io)))
-            b["reward"][...], b["cost"][...], b["done"][...] = rew, cost, done
         infos = {"assign": b["assign"], "collisions": b["cost"]}
         return b["obs"], self._graph(), b["reward"], b["cost"], b["done"], infos
 

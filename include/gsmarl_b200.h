@@ -231,6 +231,9 @@ int gsm_host_io(gsm_env* h, gsm_step_io* out);
  *   already hold zeros and rows that stop being valid are cleared — and of nbr_idx only the 16-byte
  *   pieces that differ from what the host already holds (neighbour sets change slowly), so the host
  *   arrays stay bit-identical to the device tensors.  sparse == 0: one dense D2H copy per call.
+ *   In sparse mode the library relies on the host arena holding what it last delivered: treat the output
+ *   buffers as READ-ONLY (copy before modifying in place); calling gsm_set_host_outputs again with the same
+ *   arguments forces a dense re-synchronisation if they were overwritten.
  * A change takes effect with a dense re-synchronisation on the next *_host call. */
 int gsm_set_host_outputs(gsm_env* h, uint32_t out_mask, int32_t sparse);
 int gsm_reset_host(gsm_env* h, uint64_t seed, const uint8_t* mask, int64_t mask_stride,
