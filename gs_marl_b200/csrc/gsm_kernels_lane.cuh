@@ -11,9 +11,22 @@
 // The env state stays in shared memory / registers for `n_steps` fused steps.  fp32 uses a
 // squared-distance pre-check so sqrt/softplus run only for pairs in or near contact or within
 // sensing range; fp64 evaluates every pair exactly as SPEC.md writes it.  A found neighbour
-// row goes straight to HBM over a warp-cooperative, fully coalesced clear of the row blocks.
+// row goes straight to HBM over a warp-cooperative, fully coalesced clear of the feature blocks
+// (fp32: one 16-byte and one 8-byte store per row); the rows' entity indices are collected in a
+// shared-memory list per agent and nbr_idx leaves as one coalesced store per agent.
+// Round 2 (profiles/README.md, diagnostic builds GSM_LANE_DIAG): the scattered row stores — one L1
+// pass per lane and store instruction — were 25 % of the step, instruction count was not the limit
+// (a packed-arithmetic candidate sweep over a pair table, 11 % fewer instructions, changed nothing
+// in time; it stays because it is no slower and frees issue slots).
 #pragma once
 #include "gsm_kernels_spec.cuh"
+
+#ifndef GSM_LANE_ROW16
+#define GSM_LANE_ROW16 1     // A/B: fp32 rows as a 16-byte + an 8-byte store (0: three 8-byte stores)
+#endif
+#ifndef GSM_LANE_DIAG
+#define GSM_LANE_DIAG 0      // diagnostic builds only: 1 no clear, 2 no row stores, 4 no adj / obs stores
+#endif
 
 namespace gsm {
 
@@ -35,17 +48,63 @@ __host__ __device__ inline LaneGeom lane_geom(int N) {
 // Entity tables are padded to a multiple of 8 plus 8 far-away dummies (index lane_epad(E)):
 // the pair sweeps run in fully unrolled groups of 8 without bounds checks.
 __host__ __device__ inline int lane_epad(int E) { return (E + 7) / 8 * 8; }
+// Pair table (fp32 sweeps): entity positions again, two entities per 16 bytes {x0, x1, y0, y1}, so that the
+// candidate sweep loads two entities per LDS.128 and tests them with packed fp32 arithmetic (FADD2 / FMUL2 / FFMA2).
+__host__ __device__ inline size_t lane_pair_bytes(int rb, int E) { return rb == 4 ? (size_t)(lane_epad(E) + 8) * 8 : 0; }
 __host__ __device__ inline size_t lane_env_bytes(int ent_bytes, int rb, int N, int E) {
-  return ((size_t)(lane_epad(E) + 8) * ent_bytes + 15) / 16 * 16 + ((size_t)N * 2 * rb + 15) / 16 * 16 +
+  return ((size_t)(lane_epad(E) + 8) * ent_bytes + 15) / 16 * 16 + lane_pair_bytes(rb, E) + ((size_t)N * 2 * rb + 15) / 16 * 16 +
          ((size_t)N * rb + 15) / 16 * 16;
 }
-__host__ __device__ inline size_t lane_smem(int ent_bytes, int rb, int N, int E, int envs_per_cta) {
+// Neighbour list of a lane's agent (entity indices in row order, 16 bits each): the rows' nbr_idx block leaves
+// from it as one coalesced store per agent.  Odd word stride: lanes writing entry r of their lists hit 32 banks.
+__host__ __device__ inline int lane_list_words(int K) { return ((K + 1) / 2) | 1; }
+__host__ __device__ inline size_t lane_smem(int ent_bytes, int rb, int N, int E, int K, int envs_per_cta, int warps_per_cta) {
   // per env: entity table, agent velocities, shared-reward scratch; per CTA: collider list
   // (padded to a multiple of 8) and the per-word masks of entities that count for the cost
+  // ... and 16 bytes of launch constants found while staging (collider count, largest size)
   return lane_env_bytes(ent_bytes, rb, N, E) * envs_per_cta + ((size_t)(lane_epad(E) + 8) * 4 + 15) / 16 * 16 +
-         ((size_t)((E + 31) / 32) * 4 + 15) / 16 * 16;
+         ((size_t)((E + 31) / 32) * 4 + 15) / 16 * 16 + 16 + (size_t)warps_per_cta * 32 * lane_list_words(K) * 4;
 }
 
+// Candidate mask of 8 consecutive entities (4 entries of the pair table) on the squared distance.
+template <typename T> struct PairSweep {
+  static constexpr bool kOn = false;
+  static __device__ __forceinline__ uint32_t mask8(const float4*, T, T, T) { return 0; }
+  static __device__ __forceinline__ void put(void*, int, T, T) {}
+};
+template <> struct PairSweep<float> {
+  static constexpr bool kOn = true;
+  static __device__ __forceinline__ uint32_t mask8(const float4* pp, float npx, float npy, float Rs2) {
+    const float2 nx = make_float2(npx, npx), ny = make_float2(npy, npy);
+    uint32_t m8 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float4 q = pp[k];
+      const float2 dx = __fadd2_rn(make_float2(q.x, q.y), nx), dy = __fadd2_rn(make_float2(q.z, q.w), ny);
+      const float2 d2 = __ffma2_rn(dy, dy, __fmul2_rn(dx, dx));
+      if (d2.x < Rs2) m8 |= 1u << (2 * k);
+      if (d2.y < Rs2) m8 |= 2u << (2 * k);
+    }
+    return m8;
+  }
+  static __device__ __forceinline__ void put(void* pp, int e, float x, float y) {
+    float* f = (float*)pp + 4 * (e >> 1) + (e & 1);
+    f[0] = x; f[2] = y;
+  }
+};
+
+// One neighbour row.  Scattered stores cost the L1 one pass per lane whatever their size (diagnostic builds,
+// profiles/README.md: the rows were 25 % of the step), so fp32 rows go out in two stores instead of three.
+template <typename T>
+__device__ __forceinline__ void row_store(T* f, bool al16, int odd, T a, T b, T c, T d, T e, T g) {
+  st2<T>(f, a, b); st2<T>(f + 2, c, d); st2<T>(f + 4, e, g);
+}
+template <>
+__device__ __forceinline__ void row_store<float>(float* f, bool al16, int odd, float a, float b, float c, float d, float e, float g) {
+  if (!al16) { st2<float>(f, a, b); st2<float>(f + 2, c, d); st2<float>(f + 4, e, g); }
+  else if (odd) { st2<float>(f, a, b); *reinterpret_cast<float4*>(f + 2) = make_float4(c, d, e, g); }
+  else { *reinterpret_cast<float4*>(f) = make_float4(a, b, c, d); st2<float>(f + 4, e, g); }
+}
 template <typename T> __device__ __forceinline__ void st_zero16(void* p) {
   *reinterpret_cast<int4*>(p) = make_int4(0, 0, 0, 0);
 }
@@ -91,14 +150,21 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   const int64_t env = has_env ? env_raw : 0;
 
   const int EP = lane_epad(E);                         // padded entity count; dummy index = EP
-  const size_t ent_b = ((size_t)(EP + 8) * sizeof(EntT) + 15) / 16 * 16, vel_b = ((size_t)N * 2 * sizeof(T) + 15) / 16 * 16,
-               rew_b = ((size_t)N * sizeof(T) + 15) / 16 * 16;
-  unsigned char* base = sm + (size_t)(has_env || multi ? env_l : 0) * (ent_b + vel_b + rew_b);
+  typedef PairSweep<T> PS;
+  const size_t ent_b = ((size_t)(EP + 8) * sizeof(EntT) + 15) / 16 * 16, pair_b = lane_pair_bytes((int)sizeof(T), E),
+               vel_b = ((size_t)N * 2 * sizeof(T) + 15) / 16 * 16, rew_b = ((size_t)N * sizeof(T) + 15) / 16 * 16;
+  unsigned char* base = sm + (size_t)(has_env || multi ? env_l : 0) * (ent_b + pair_b + vel_b + rew_b);
   EntT* ent = (EntT*)base;
-  T* vel = (T*)(base + ent_b);
-  T* rew = (T*)(base + ent_b + vel_b);
-  int* clist = (int*)(sm + (size_t)g.envs_per_cta * (ent_b + vel_b + rew_b));
+  float4* pairs = (float4*)(base + ent_b);             // fp32 only (pair_b = 0 otherwise)
+  T* vel = (T*)(base + ent_b + pair_b);
+  T* rew = (T*)(base + ent_b + pair_b + vel_b);
+  int* clist = (int*)(sm + (size_t)g.envs_per_cta * (ent_b + pair_b + vel_b + rew_b));
   uint32_t* costmask = (uint32_t*)((unsigned char*)clist + ((size_t)(EP + 8) * 4 + 15) / 16 * 16);
+  uint32_t* meta = (uint32_t*)((unsigned char*)costmask + ((size_t)((E + 31) / 32) * 4 + 15) / 16 * 16);   // [0] colliders, [2..] largest size
+  const int lw = lane_list_words(K);
+  uint16_t* wlist = (uint16_t*)(meta + 4) + (size_t)warp * 32 * lw * 2;   // this warp's 32 neighbour lists
+  uint16_t* elist = wlist + (size_t)lane * lw * 2;                        // mine
+  const unsigned list_sa = (unsigned)__cvta_generic_to_shared(wlist);
 
   // ---- stage: entity tables (each env by its own lanes / CTA), collider list ------------------
   {
@@ -113,13 +179,16 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         else { q.x = (T)1e18; q.y = (T)1e18; }         // dummy: never near anything
         q.size = e < E ? p.size[e] : (T)0; q.flag = e < E ? (int)p.eflag[e] : 0;
         ent[e] = q;
+        PS::put(pairs, e, q.x, q.y);
       }
     }
     if (warp == 0) {
       int n = 0;
+      T ms = 0;
       for (int e0 = 0; e0 < E; e0 += 32) {
         const int e = e0 + lane;
         const int fl = e < E ? (int)p.eflag[e] : 0;
+        if (e < E) { const T sz = p.size[e]; ms = sz > ms ? sz : ms; }
         const bool c = fl & 1;
         const unsigned b = __ballot_sync(0xffffffffu, c);
         if (c) clist[n + __popc(b & low_mask(lane))] = e;
@@ -130,12 +199,14 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         if (lane == 0) costmask[e0 >> 5] = cb;
       }
       for (int k = n + lane; k < (n + 7) / 8 * 8; k += 32) clist[k] = EP;   // pad with the dummy
+#pragma unroll
+      for (int o = 16; o; o >>= 1) { const T v = __shfl_xor_sync(0xffffffffu, ms, o); ms = v > ms ? v : ms; }
+      if (lane == 0) { meta[0] = (uint32_t)n; *(T*)(meta + 2) = ms; }
     }
   }
   __syncthreads();
-  int nc = 0;
-  T max_size = 0;
-  for (int e = 0; e < E; e++) { nc += (p.eflag[e] & 1); const T sz = p.size[e]; max_size = sz > max_size ? sz : max_size; }
+  const int nc = (int)meta[0];
+  const T max_size = *(const T*)(meta + 2);
   // every contact distance below the sensing radius: a colliding pair is a neighbour candidate
   // anyway, so the candidate sweep needs one squared-distance test per pair instead of two
   const bool col_in_nb = ((T)2 * max_size) * (T)1.0001 < p.Rs;
@@ -167,7 +238,6 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   // output cursors of my agent
   const unsigned char* c_act = (const unsigned char*)p.actions +
       (p.action_mode == GSM_ACT_DISCRETE ? row * 4 : row * 2 * (int64_t)sizeof(T));
-  unsigned char* c_idx = (unsigned char*)(p.nbr_idx + row * K);
   unsigned char* c_feat = (unsigned char*)(p.nbr_feat + row * K * GSM_NBR_FEAT_DIM);
   unsigned char* c_obs = (unsigned char*)(p.obs + row * GSM_OBS_DIM);
   unsigned char* c_cnt = (unsigned char*)(p.nbr_cnt + row);
@@ -176,6 +246,13 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
   unsigned char* c_cost = (unsigned char*)(p.cost + row);
   unsigned char* c_done = (unsigned char*)(p.done + row);
   unsigned char* c_asg = (unsigned char*)(p.assign + row);
+  // fp32 rows (24 bytes) leave as a 16-byte and an 8-byte store (which first depends on the row's parity) when
+  // my agent's block is 16-byte aligned in every slot.  Measured (one launch, us per step, two stores / three):
+  // nav-6 15.3 / 18.1, nav-12 21.8 / 24.4, nav-24 24.1 / 24.5, but nav-48 61.8 / 56.7 and nav-96 132.3 / 122.9 —
+  // envs that span several warps keep the three 8-byte stores.
+  const bool feat16 = GSM_LANE_ROW16 && !CARRY && !multi && sizeof(T) == 4 &&   // (!CARRY: compiled out of the large-team instances)
+      ((((uintptr_t)c_feat) | (uintptr_t)ss.nbr_feat) & 15) == 0;
+  const int idx_a0 = lane / K, idx_k0 = lane - idx_a0 * K, idx_da = 32 / K, idx_dk = 32 - idx_da * K;
   unsigned char* c_idx_base = (unsigned char*)p.nbr_idx;   // slot bases for the warp-wide clears
   unsigned char* c_feat_base = (unsigned char*)p.nbr_feat;
 
@@ -238,13 +315,15 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     }
     t_now += 1;
     if (multi) __syncthreads(); else __syncwarp();     // everyone has read the old table
-    if (active) { ent[i].x = px; ent[i].y = py; vel[2 * i] = vx; vel[2 * i + 1] = vy; }
+    if (active) { ent[i].x = px; ent[i].y = py; vel[2 * i] = vx; vel[2 * i + 1] = vy; PS::put(pairs, i, px, py); }
     if (multi) __syncthreads(); else __syncwarp();
 
     // ---- padding first: the rows of this warp's agents are one contiguous region of nbr_idx /
     // nbr_feat, so the warp clears it with fully coalesced 16-byte stores (-1 / zeros); the few
     // real neighbour rows are written over it after the __syncwarp.  (Per-lane padding loops cost
     // L1TEX one line per lane per instruction: ncu_r1_lane24.)
+    int64_t w_row0;
+    int w_nrows;
     {
       int64_t row0, nrows;
       if (multi) { row0 = env * N + warp * 32; nrows = N - warp * 32; nrows = nrows > 32 ? 32 : (nrows < 0 ? 0 : nrows); }
@@ -254,17 +333,13 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         ne = ne > g.envs_per_warp ? g.envs_per_warp : (ne < 0 ? 0 : ne);
         row0 = envw * N; nrows = ne * N;
       }
-      unsigned char* zi = c_idx_base + row0 * K * 4;
-      const int64_t bi = nrows * K * 4;
-      if ((((uintptr_t)zi | (uintptr_t)bi) & 15) == 0) {
-        for (int64_t q = (int64_t)lane * 16; q < bi; q += 512) *reinterpret_cast<int4*>(zi + q) = make_int4(-1, -1, -1, -1);
-      } else {
-        for (int64_t q = (int64_t)lane * 4; q < bi; q += 128) *reinterpret_cast<int32_t*>(zi + q) = -1;
-      }
+      if (GSM_LANE_DIAG & 1) nrows = 0;
+      w_row0 = row0; w_nrows = (int)nrows;
       unsigned char* zf = c_feat_base + row0 * K * GSM_NBR_FEAT_DIM * (int64_t)sizeof(T);
       const int64_t bf = nrows * K * GSM_NBR_FEAT_DIM * (int64_t)sizeof(T);
       if ((((uintptr_t)zf | (uintptr_t)bf) & 15) == 0) {
-        for (int64_t q = (int64_t)lane * 16; q < bf; q += 512) st_zero16<T>(zf + q);
+        unsigned char* z = zf + lane * 16;                 // (a warp's block is < 2^31 bytes)
+        for (int q = lane * 16, n = (int)bf; q < n; q += 512, z += 512) st_zero16<T>(z);
       } else {
         for (int64_t q = (int64_t)lane * sizeof(T); q < bf; q += 32 * sizeof(T)) *reinterpret_cast<T*>(zf + q) = (T)0;
       }
@@ -284,6 +359,10 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       const int goal_e = p.own_goal_always ? N + i : -1;
       for (int e0 = 0; e0 < E; e0 += 32) {
         uint32_t cand = 0;
+        if (PS::kOn && col_in_nb) {                    // fp32: two entities per load, packed arithmetic
+          for (int g0 = 0; g0 < 32 && e0 + g0 < E; g0 += 8)
+            cand |= PS::mask8(pairs + ((e0 + g0) >> 1), -px, -py, Rs2) << g0;
+        } else
         for (int g0 = 0; g0 < 32 && e0 + g0 < E; g0 += 8) {
           uint32_t m8 = 0;
 #pragma unroll
@@ -321,17 +400,17 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
           }
           if (dist < p.Rs || e == goal_e) {
             word |= 1u << k;
-            if (cnt < K) {
+            if (cnt < K && !((GSM_LANE_DIAG & 2) && cnt > 0)) {
               T evx = 0, evy = 0;
               if (e < N) { evx = vel[2 * e]; evy = vel[2 * e + 1]; }
-              ((int32_t*)c_idx)[cnt] = e;
+              elist[cnt] = (uint16_t)e;
               T* f = (T*)c_feat + cnt * GSM_NBR_FEAT_DIM;
-              st2<T>(f, dx, dy); st2<T>(f + 2, evx - vx, evy - vy); st2<T>(f + 4, dist, (T)(q.flag >> 1));
+              row_store<T>(f, feat16, cnt & 1, dx, dy, evx - vx, evy - vy, dist, (T)(q.flag >> 1));
             }
             cnt++;
           }
         }
-        ((uint32_t*)c_adj)[e0 >> 5] = word;
+        if (!(GSM_LANE_DIAG & 4) || e0 == 0) ((uint32_t*)c_adj)[e0 >> 5] = word;
       }
       if (cnt > K) cnt = K;
       const T gx = gxl - px, gy = gyl - py;
@@ -345,6 +424,39 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       *(int32_t*)c_asg = i;
       if (!p.share_reward) *(T*)c_rew = r;
     }
+    // ---- nbr_idx: the warp's rows are one contiguous block of w_nrows * K words; pass q writes words
+    //      [32 q, 32 q + 32) from the agents' neighbour lists (-1 from cnt on), fully coalesced ---------------
+    __syncwarp();
+    {
+      const int npass = (w_nrows * K + 31) >> 5, last = w_nrows * K - lane;   // my word exists while 32 q < last
+      int32_t* gi = (int32_t*)c_idx_base + w_row0 * K + lane;
+      unsigned sl = list_sa + (unsigned)(idx_a0 * lw * 2 + idx_k0) * 2u;       // shared address of my list entry
+      int a = idx_a0;
+      if (idx_dk == 0) {                                   // K divides 32 (8, 16, 32): my row number never changes
+        const unsigned dsl = (unsigned)(idx_da * lw * 4);
+        for (int q = 0; q < npass; q++) {
+          const int cnt_a = __shfl_sync(0xffffffffu, cnt, a);
+          unsigned v;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(sl) : "memory");
+          if ((q << 5) < last) *gi = idx_k0 < cnt_a ? (int32_t)v : -1;
+          a += idx_da; sl += dsl; gi += 32;
+        }
+      } else {
+        int k = idx_k0;
+        for (int q = 0; q < npass; q++) {
+          const int cnt_a = __shfl_sync(0xffffffffu, cnt, a);
+          unsigned v;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(sl) : "memory");
+          if ((q << 5) < last) *gi = k < cnt_a ? (int32_t)v : -1;
+          a += idx_da; k += idx_dk;
+          const bool wrap = k >= K;
+          k -= wrap ? K : 0; a += wrap ? 1 : 0;
+          sl += (unsigned)(idx_da * lw * 4 + idx_dk * 2) + (wrap ? (unsigned)(lw * 4 - K * 2) : 0u);
+          gi += 32;
+        }
+      }
+    }
+    __syncwarp();
     if (p.share_reward) {                              // mean over the env's agents, ascending order
       if (active) rew[i] = r;
       if (multi) __syncthreads(); else __syncwarp();
@@ -363,10 +475,12 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         spawn_draw<T>(genv, ep, i, p.seed, p.ext[GSM_ENT_AGENT], px, py);
         vx = 0; vy = 0;
         ent[i].x = px; ent[i].y = py; vel[2 * i] = 0; vel[2 * i + 1] = 0;
+        PS::put(pairs, i, px, py);
         for (int l = i; l < L; l += N) {
           T x, y;
           spawn_draw<T>(genv, ep, N + l, p.seed, p.ext[ent[N + l].flag >> 1], x, y);
           ent[N + l].x = x; ent[N + l].y = y;
+          PS::put(pairs, N + l, x, y);
         }
       }
       if (multi) __syncthreads(); else __syncwarp();
@@ -375,7 +489,7 @@ env_lane_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     } else {
       have_carry = want_carry;
     }
-    c_act += ss.actions; c_idx += ss.nbr_idx; c_feat += ss.nbr_feat; c_obs += ss.obs;
+    c_act += ss.actions; c_feat += ss.nbr_feat; c_obs += ss.obs;
     c_cnt += ss.nbr_cnt; c_adj += ss.adj; c_rew += ss.reward; c_cost += ss.cost;
     c_done += ss.done; c_asg += ss.assign;
     c_idx_base += ss.nbr_idx; c_feat_base += ss.nbr_feat;

@@ -269,8 +269,8 @@ int GSM_SFX(launch_lane)(const HostParams& hp, const gsm_step_io& io, int n_step
   ss.nbr_cnt = rs.nbr_cnt; ss.adj = rs.adj; ss.reward = rs.reward; ss.cost = rs.cost;
   ss.done = rs.done; ss.assign = rs.assign;
   const LaneGeom g = lane_geom(hp.N);
-  const size_t smem = lane_smem((int)sizeof(LaneEnt<GSM_REAL>), (int)sizeof(GSM_REAL), hp.N, hp.N + hp.L,
-                                g.envs_per_cta);
+  const size_t smem = lane_smem((int)sizeof(LaneEnt<GSM_REAL>), (int)sizeof(GSM_REAL), hp.N, hp.N + hp.L, hp.K,
+                                g.envs_per_cta, g.warps_per_cta);
   const bool carry = sizeof(GSM_REAL) == 4 && hp.N >= env_int("GSM_LANE_CARRY_MIN_N", 48);
   auto k = carry ? (hp.auto_reset ? env_lane_kernel<GSM_REAL, true, true> : env_lane_kernel<GSM_REAL, false, true>)
                  : (hp.auto_reset ? env_lane_kernel<GSM_REAL, true, false> : env_lane_kernel<GSM_REAL, false, false>);
