@@ -13,6 +13,7 @@
 // HBM over a warp-cooperative coalesced clear like in env_lane_kernel, and `n_steps` steps are fused.
 #pragma once
 #include "gsm_kernels_spec.cuh"
+#include "gsm_kernels_lane.cuh"   // row_store
 
 namespace gsm {
 
@@ -210,6 +211,9 @@ __host__ __device__ inline size_t team_env_bytes(int rb, int N) {
   return ((size_t)(4 * N + N * N + N) * rb + (size_t)team_lsa_smem(rb, N).words * 4 + 15) / 16 * 16;
 }
 
+#ifndef GSM_TEAM_ROW16         // A/B: fp32 rows as a 16-byte + an 8-byte store (lane kernel, profiles/README.md)
+#define GSM_TEAM_ROW16 1
+#endif
 #ifndef GSM_TEAM_BLOCKS        // A/B: resident CTAs per SM the fp32 instances are compiled for (4 -> 128 registers)
 #define GSM_TEAM_BLOCKS 4
 #endif
@@ -395,6 +399,7 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
       uint32_t word = 0;
       int32_t* g_idx = (int32_t*)c_idx + row * K;
       T* g_feat = (T*)c_feat + row * K * GSM_NBR_FEAT_DIM;
+      const bool feat16 = GSM_TEAM_ROW16 && A == 1 && sizeof(T) == 4 && (((uintptr_t)g_feat) & 15) == 0;   // A = 3 (N = 12): measured slower (polygon-12 68.9 vs 63.0 us)
       for (int e = 0; e < E; e++) {
         if (e == i) continue;
         T ex, ey, evx = 0, evy = 0, es;
@@ -409,7 +414,7 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
           if (cnt < K && live) {
             g_idx[cnt] = e;
             T* f = g_feat + cnt * GSM_NBR_FEAT_DIM;
-            st2<T>(f, dx, dy); st2<T>(f + 2, evx - vx[a], evy - vy[a]); st2<T>(f + 4, dist, (T)(fl >> 1));
+            row_store<T>(f, feat16, cnt & 1, dx, dy, evx - vx[a], evy - vy[a], dist, (T)(fl >> 1));   // fp32: 16 + 8 bytes
           }
           cnt++;
         }
