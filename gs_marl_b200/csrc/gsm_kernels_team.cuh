@@ -201,6 +201,106 @@ __device__ __forceinline__ void lsa_group2(const T* __restrict__ C, uint32_t* __
   for (int a = 0; a < A; a++) c4r_out[a] = live ? ((const int*)(ws + L.c4r))[col0 + a] : -1;
 }
 
+// ---- N = 6, fp32: exhaustive solve with a uniqueness certificate ---------------------------------------------
+// 6! = 720 assignments; working lane g of the group takes the 120 with row 0 -> column g: its 5 x 5 sub-matrix
+// (rows 1..5, the columns other than g in ascending order) sits in registers and the enumeration is straight-line
+// code with compile-time indices — rows 1..3 as a prefix tree (5 + 20 + 60 partial sums), rows 4, 5 as the cheaper
+// of the two completions of the remaining column pair; best total, second best total and the best prefix number
+// are tracked with min / max / select, no dependent chain longer than a sum, no shared-memory state.
+// The result is taken only if the best total beats EVERY other one (the other completion of the winning prefix
+// included) by GSM_TEAM_ENUM6_TOL = 2e-5 of the largest matrix entry: the enumeration's own rounding is below 2e-6
+// of it (five additions), scipy's shortest-augmenting-path arithmetic in fp32 moves its path costs by ~1e-6 of it
+// (worst-case bound of the same order as the margin, SPEC.md §9 deviation 7), so scipy's answer is this one;
+// otherwise — ties, near-ties — the warp runs scipy's own procedure (lsa_group2).  Measured (profiles/README.md):
+// the certificate fails for 0.2 % (polygon) / 1.4 % (line) of the env-steps; a fallback is expensive (a lone
+// latency-bound solve), which is why the margin is not wider.  fp64 (verification) always runs lsa_group2.
+#ifndef GSM_TEAM_ENUM6
+#define GSM_TEAM_ENUM6 1       // 0: off.  Diagnostic builds: 2 no fallback (timing only), 3 = 2 + failure flag in bit 1 of `done`
+#endif
+#ifndef GSM_TEAM_ENUM6_TOL
+#define GSM_TEAM_ENUM6_TOL 2e-5f
+#endif
+template <int GP>
+__device__ __forceinline__ bool lsa_enum6(const float* __restrict__ C, int g, int base, int& col_out) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const bool has = g < 6;
+  const int gg = has ? g : 0;
+  float M[5][5];
+  const float c0 = C[gg];
+  float cmax = c0;
+#pragma unroll
+  for (int r = 0; r < 5; r++)
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      M[r][j] = C[(r + 1) * 6 + j + (j >= gg ? 1 : 0)];
+      cmax = fmaxf(cmax, M[r][j]);
+    }
+  float Smin[5][5];                                        // completions of rows 4, 5 for every column pair p < q
+#pragma unroll
+  for (int pp = 0; pp < 5; pp++)
+#pragma unroll
+    for (int q = pp + 1; q < 5; q++) Smin[pp][q] = fminf(M[3][pp] + M[4][q], M[3][q] + M[4][pp]);
+  const float inf = __int_as_float(0x7f800000);
+  float best = inf, second = inf;
+  int id = 0;
+#pragma unroll
+  for (int j0 = 0; j0 < 5; j0++) {
+    const float a = c0 + M[0][j0];
+#pragma unroll
+    for (int j1 = 0; j1 < 5; j1++) {
+      if (j1 == j0) continue;
+      const float b = a + M[1][j1];
+#pragma unroll
+      for (int j2 = 0; j2 < 5; j2++) {
+        if (j2 == j0 || j2 == j1) continue;
+        int pp = -1, q = -1;
+#pragma unroll
+        for (int c = 0; c < 5; c++) if (c != j0 && c != j1 && c != j2) { if (pp < 0) pp = c; else q = c; }
+        const int r1 = j1 - (j1 > j0 ? 1 : 0);                              // rank of j1 among the 4 left
+        const int r2 = j2 - (j2 > j0 ? 1 : 0) - (j2 > j1 ? 1 : 0);          // rank of j2 among the 3 left
+        const float t = (b + M[2][j2]) + Smin[pp][q];
+        id = t < best ? j0 * 12 + r1 * 3 + r2 : id;
+        second = fminf(second, fmaxf(best, t));
+        best = fminf(best, t);
+      }
+    }
+  }
+  if (!has) { best = inf; second = inf; }
+  const float mine = best;
+#pragma unroll
+  for (int m = GP / 2; m >= 1; m >>= 1) {                  // best / second best / largest entry over the group
+    const float ob = __shfl_xor_sync(FULL, best, m), os = __shfl_xor_sync(FULL, second, m);
+    second = fminf(fminf(second, os), fmaxf(best, ob));
+    best = fminf(best, ob);
+    cmax = fmaxf(cmax, __shfl_xor_sync(FULL, cmax, m));
+  }
+  const unsigned winners = (__ballot_sync(FULL, has && mine == best) >> base) & ((1u << GP) - 1u);
+  const int gw = winners ? __ffs(winners) - 1 : 0;                            // row 0 -> column gw
+  const float margin = GSM_TEAM_ENUM6_TOL * cmax;
+  bool ok = winners != 0 && second - best > margin;
+  // the winner decodes its prefix, settles the completion on the two sums and checks the other completion
+  unsigned packed = 0;
+  if (g == gw) {
+    const int j0 = id / 12, r1 = (id - j0 * 12) / 3, r2 = id - j0 * 12 - r1 * 3;
+    const int j1 = r1 + (r1 >= j0 ? 1 : 0);
+    int j2 = r2;                                                              // r2-th of the columns other than j0, j1
+    { const int lo = j0 < j1 ? j0 : j1, hi = j0 < j1 ? j1 : j0; if (j2 >= lo) j2++; if (j2 >= hi) j2++; }
+    unsigned left = 31u & ~(1u << j0) & ~(1u << j1) & ~(1u << j2);
+    const int pp = __ffs(left) - 1; left &= left - 1;
+    const int q = __ffs(left) - 1;
+    const int cj0 = j0 + (j0 >= g ? 1 : 0), cj1 = j1 + (j1 >= g ? 1 : 0), cj2 = j2 + (j2 >= g ? 1 : 0);
+    const int cp = pp + (pp >= g ? 1 : 0), cq = q + (q >= g ? 1 : 0);
+    const float s1 = C[4 * 6 + cp] + C[5 * 6 + cq], s2 = C[4 * 6 + cq] + C[5 * 6 + cp];
+    const bool sw = s2 < s1;
+    if (!(fabsf(s1 - s2) > margin)) ok = false;
+    packed = (unsigned)g | ((unsigned)cj0 << 3) | ((unsigned)cj1 << 6) | ((unsigned)cj2 << 9) |
+             ((unsigned)(sw ? cq : cp) << 12) | ((unsigned)(sw ? cp : cq) << 15) | (ok ? 0u : 0x80000000u);
+  }
+  packed = __shfl_sync(FULL, packed, base + gw);
+  col_out = has ? (int)((packed >> (3 * g)) & 7u) : -1;
+  return ok && !(packed >> 31);
+}
+
 // A warm-started variant (Bellman-Ford re-centred duals, free rows, uniqueness certificate, cold fallback) was built
 // on lsa_augment, is parity-green and not faster: profiles/rejected/team_warm_start_lsa_r2.diff, profiles/README.md.
 
@@ -359,11 +459,21 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
     }
     __syncwarp();
     int c4r[A];
+    bool enum_fail = false;                                // (diagnostic builds: GSM_TEAM_ENUM6 = 3 reports it in bit 1 of `done`)
 #ifdef GSM_TEAM_NO_LSA   // diagnostic build only (profiles/README.md): what the step costs without the solve
 #pragma unroll
     for (int a = 0; a < A; a++) c4r[a] = ga * A + a;
 #else
-    lsa_group2<T, N, G, GP>(cmat, (uint32_t*)(rsm + N), g, base, true, c4r);
+    // (polygon only: with the collinear slots of `line` 1.2 % of the env-steps fail the certificate, 4.9 % of the warps fall
+    //  back, and one launch is slower than without the enumeration — 21.5 vs 19.7 us per step)
+    if constexpr (GSM_TEAM_ENUM6 != 0 && SCN == GSM_SCN_POLYGON && N == 6 && G == 6 && sizeof(T) == 4) {
+      const bool certified = lsa_enum6<GP>((const float*)cmat, g, base, c4r[0]);
+      enum_fail = !certified;
+      if (GSM_TEAM_ENUM6 < 2 && __any_sync(0xffffffffu, !certified))   // a tie or near-tie somewhere in the warp: scipy's own procedure (2: timing-only build without it)
+        lsa_group2<T, N, G, GP>(cmat, (uint32_t*)(rsm + N), g, base, true, c4r);
+    } else {
+      lsa_group2<T, N, G, GP>(cmat, (uint32_t*)(rsm + N), g, base, true, c4r);
+    }
 #endif
     __syncwarp();
 
@@ -439,7 +549,7 @@ env_team_kernel(const __grid_constant__ KParams<T> p, const int n_steps,
         ((int32_t*)c_cnt)[row] = cnt;
         ((uint32_t*)c_adj)[row] = word;
         ((T*)c_cost)[row] = (T)ncol;
-        c_done[row] = (uint8_t)(t_now >= p.episode_length);
+        c_done[row] = (uint8_t)(t_now >= p.episode_length) | (uint8_t)(GSM_TEAM_ENUM6 == 3 && enum_fail ? 2 : 0);
         ((int32_t*)c_asg)[row] = c4r[a];
         if (!p.share_reward) ((T*)c_rew)[row] = rew[a];
       }

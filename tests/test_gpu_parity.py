@@ -668,6 +668,39 @@ def test_fixed_size_env_variants_and_spaces():
     c.close()
 
 
+def test_team_kernel_enumeration_equals_scipy_order_instance_f32(monkeypatch):
+    """fp32 polygon-6: the default instance solves the assignment by exhaustive enumeration and takes the result
+    only under a uniqueness certificate (else scipy's procedure, lsa_group2); the G = 3 instance always runs
+    scipy's procedure.  Same states -> every output bit-identical, including envs that start on exact ties
+    (agents halfway between slots, agents on the slots in reversed order) and 25 steps of random motion."""
+    from oracle import gsm_oracle as O
+    cfg = make_cfg("polygon", 6, "f32")
+    B, T, N = 515, 25, 6
+    o = O.OracleEnv(cfg, B)
+    o.reset(23)
+    ang = (2 * np.arange(N) + 1) * np.pi / N
+    ring = cfg.polygon_radius * np.stack([np.cos(ang), np.sin(ang)], -1)
+    o.agent_state[:40, :, :2] = o.landmark_pos[:40, :1, :] + ring[None]                      # two equally good shifts
+    o.agent_state[40:60, :, :2] = o.landmark_pos[40:60, :1, :] + 3.0 * ring[None]            # far ring: near-ties
+    sl = o.landmark_pos[60:80, :1, :] + cfg.polygon_radius * np.asarray(cfg.slot_table).reshape(N, 2)[None]
+    o.agent_state[60:80, :, :2] = sl[:, ::-1, :]                                             # on the slots, reversed
+    o.agent_state[:80, :, 2:] = 0
+    acts = random_actions(cfg, np.random.default_rng(4), (T, B))
+    acts[0] = 0
+    outs = []
+    for team_g in (None, "3"):
+        if team_g:
+            monkeypatch.setenv("GSM_TEAM_G", team_g)
+        env = _env(cfg, B)
+        env.set_state(o.agent_state, o.landmark_pos, o.step_count)
+        outs.append(_np(env.rollout(acts)))
+        env.close()
+    for k in OUT_KEYS:
+        assert outs[0][k].tobytes() == outs[1][k].tobytes(), k
+    a = outs[0]["assign"][..., 0] if outs[0]["assign"].ndim == 4 else outs[0]["assign"]
+    assert (np.sort(a.reshape(T, B, N), axis=2) == np.arange(N)).all()                       # permutations
+
+
 @pytest.mark.parametrize("name,N", [("polygon", 3), ("polygon", 4), ("polygon", 5), ("polygon", 6), ("polygon", 12),
                                     ("line", 3), ("line", 4), ("line", 5), ("line", 6), ("line", 12)])
 @pytest.mark.parametrize("kw", [{}, {"share_reward": True, "max_nbrs": 2}, {"team_g": 2}, {"team_g": 3}])
