@@ -318,7 +318,8 @@ __host__ __device__ inline size_t team_env_bytes(int rb, int N) {
 #define GSM_TEAM_BLOCKS 4
 #endif
 #ifndef GSM_TEAM_BLOCKS_A1     // ... of the one-agent-per-lane instances (N = 6, polygon, one launch / 4 streams: 4 CTAs 22.4 /
-#define GSM_TEAM_BLOCKS_A1 5   //     16.1 us, 5 CTAs 17.9 / 16.4, 6 CTAs 19.6 / 17.9, 7 CTAs 23.0 / 21.2)
+#define GSM_TEAM_BLOCKS_A1 5   //     16.1 us, 5 CTAs 17.9 / 16.4, 6 CTAs 19.6 / 17.9, 7 CTAs 23.0 / 21.2; with lsa_enum6: 4 CTAs 13.4 / 10.8,
+                               //     5 CTAs (96 registers) 12.9 / 10.2, 6 CTAs (78) 15.2 / 11.8)
 #endif
 template <typename T, int A> struct TeamMinBlocks {
   static constexpr int value = sizeof(T) != 4 ? 1 : (A == 1 ? GSM_TEAM_BLOCKS_A1 : GSM_TEAM_BLOCKS);
